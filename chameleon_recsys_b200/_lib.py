@@ -1,0 +1,123 @@
+"""ctypes binding of libnar_b200.so (include/nar_b200.h).  There is no fallback: if the
+library is missing or no sm_100 device is present, loading / ctx creation raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libnar_b200.so')
+
+NAR_MAX_SEGMENTS = 24
+NAR_MAX_SRC = 16
+
+ACT_NONE, ACT_LEAKY, ACT_TANH = 0, 1, 2
+
+
+class NarError(RuntimeError):
+    pass
+
+
+class Segment(C.Structure):
+    _fields_ = [('kind', C.c_int32), ('col', C.c_int32), ('width', C.c_int32), ('card', C.c_int32),
+                ('src', C.c_int32), ('ld', C.c_int32), ('table', C.c_void_p), ('grad', C.c_void_p)]
+
+
+class FeaturePlanC(C.Structure):
+    _fields_ = [('n_segments', C.c_int32), ('row_ld', C.c_int32),
+                ('seg', Segment * NAR_MAX_SEGMENTS),
+                ('ctx_int', C.c_void_p * NAR_MAX_SRC),
+                ('ctx_float', C.c_void_p * NAR_MAX_SRC),
+                ('meta', C.c_void_p * NAR_MAX_SRC),
+                ('created_at_ts', C.c_void_p), ('pop_norm', C.c_void_p),
+                ('gamma', C.c_void_p), ('beta', C.c_void_p), ('stats', C.c_void_p),
+                ('log_base_recency', C.c_float), ('log_base_novelty', C.c_float)]
+
+
+class GemmEpilogue(C.Structure):
+    _fields_ = [('bias', C.c_void_p), ('act', C.c_int32), ('dact', C.c_int32), ('aux', C.c_void_p),
+                ('ld_aux', C.c_int64), ('accumulate', C.c_int32), ('split_k', C.c_int32),
+                ('precision', C.c_int32)]
+
+
+_lib: Optional[C.CDLL] = None
+
+i64, i32, f32, vp, u64, u32 = C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_uint64, C.c_uint32
+
+_SIGNATURES = {
+    'nar_abi_version': (C.c_int, []),
+    'nar_status_string': (C.c_char_p, [C.c_int]),
+    'nar_ctx_create': (C.c_int, [C.c_int, C.POINTER(vp)]),
+    'nar_ctx_destroy': (C.c_int, [vp]),
+    'nar_gather_features': (C.c_int, [vp, C.POINTER(FeaturePlanC), vp, vp, i64, i64, i64, vp, vp, vp, vp]),
+    'nar_gather_features_bwd': (C.c_int, [vp, C.POINTER(FeaturePlanC), vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, vp]),
+    'nar_feature_stats': (C.c_int, [vp, vp, i64, i64, vp, vp, vp, f32, f32, vp, vp, i64, i64, i64, vp, vp, vp]),
+    'nar_gather_rows_f32': (C.c_int, [vp, i64, i64, C.c_int, vp, i64, vp, i64, vp]),
+    'nar_scatter_add_rows_f32': (C.c_int, [vp, i64, i64, C.c_int, vp, i64, vp, i64, vp]),
+    'nar_gemm_tf32': (C.c_int, [vp, i64, i64, i64, vp, i64, C.c_int, vp, i64, C.c_int, vp, i64,
+                                C.POINTER(GemmEpilogue), vp]),
+    'nar_ugrnn_fwd': (C.c_int, [vp, vp, vp, vp, i64, i64, vp, vp, vp, vp]),
+    'nar_ugrnn_bwd': (C.c_int, [vp, vp, vp, vp, vp, vp, vp, i64, i64, vp, vp, vp]),
+    'nar_sample_negatives_workspace': (C.c_int, [i64, i64, i64, i64, C.POINTER(i64)]),
+    'nar_sample_negatives': (C.c_int, [vp, vp, i64, i64, i64, i64, vp, i64, i64, i64, u64, u32, vp, vp, i64, vp]),
+    'nar_mul_pred': (C.c_int, [vp, vp, i64, i64, i64, vp, vp]),
+    'nar_mul_pred_bwd': (C.c_int, [vp, vp, vp, i64, i64, i64, vp, vp, vp]),
+    'nar_score_softmax_ce': (C.c_int, [vp, i64, i64, vp, i64, vp, i64, i64, f32, f32, vp, vp, vp, vp, vp, vp]),
+    'nar_cosine_softmax_ce': (C.c_int, [vp, vp, i64, i64, i64, f32, f32, vp, vp, vp, vp, vp]),
+    'nar_colsum_add': (C.c_int, [vp, i64, i64, i64, vp, vp]),
+    'nar_act_bwd': (C.c_int, [vp, vp, i64, C.c_int, vp, vp]),
+    'nar_l2_loss_add': (C.c_int, [vp, i64, f32, vp, vp]),
+    'nar_transpose_f32': (C.c_int, [vp, i64, i64, i64, vp, i64, vp]),
+    'nar_adam_tf': (C.c_int, [vp, vp, vp, vp, i64, i64, f32, f32, f32, f32, f32, i64, vp]),
+}
+
+EXPORTED_SYMBOLS = sorted(_SIGNATURES.keys())
+
+
+def load() -> C.CDLL:
+    """Load the shared library (no GPU needed for this step); raises if it was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NarError('libnar_b200.so is not built (%s). Run __graft_entry__.build() / '
+                       'python -m chameleon_recsys_b200.build ; there is no CPU fallback.' % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.nar_abi_version() != 1:
+        raise NarError('ABI version mismatch')
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ''):
+    if rc != 0:
+        msg = load().nar_status_string(rc)
+        raise NarError('%s failed: %d (%s)' % (what or 'libnar_b200 call', rc, msg.decode() if msg else '?'))
+
+
+class Context:
+    """Owns a nar_ctx for one device.  Raises when no sm_100 device is available."""
+
+    def __init__(self, device: int = 0):
+        lib = load()
+        h = vp()
+        check(lib.nar_ctx_create(int(device), C.byref(h)), 'nar_ctx_create')
+        self.lib = lib
+        self.handle = h
+        self.device = device
+
+    def close(self):
+        if self.handle:
+            self.lib.nar_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,395 @@
+// TMA-fed tcgen05 (kind::tf32) GEMM with fused epilogues for the NAR dense layers.
+//
+//   D[M,N] = epilogue( sum_k A(m,k) * B(n,k) )
+//
+// Replaces every tf.layers.Dense of the reference graph (nar_model.py:375-473) and the UGRNN
+// input projection (:1317); forward, dgrad and wgrad all go through this one kernel by
+// choosing operand majors (no transposed copies of weights or activations are ever made):
+//   fwd   Y  = X  * W        A = X  (K-major)   B = W   (MN-major: W is [in,out], out contiguous)
+//   dgrad dX = dY * W^T      A = dY (K-major)   B = W   (K-major)
+//   wgrad dW = X^T * dY      A = X  (MN-major)  B = dY  (MN-major), split-K + red.add
+//
+// CTA = 256 threads, one 128x128 fp32 accumulator tile in TMEM (128 columns):
+//   warp 0    TMA producer  (cp.async.bulk.tensor.2d, SWIZZLE_128B, 32 fp32 = 128 B per row)
+//   warp 1    MMA issuer    (one thread, tcgen05.mma.cta_group::1.kind::tf32, M=128 N=128 K=8)
+//   warp 2    TMEM allocator
+//   warps 4-7 3xTF32 operand split (lo = x - tf32_trunc(x), written next to the TMA tile)
+//             during the main loop, then the epilogue (tcgen05.ld 32x32b -> bias/activation/
+//             activation-derivative -> st.global.v4 or red.global.add).
+// 3xTF32: the tensor core reads fp32 bits as tf32 by dropping the low 13 mantissa bits, so the
+// "hi" operand is the TMA tile itself; D += Ahi*Bhi + Alo*Bhi + Ahi*Blo restores ~fp32 accuracy
+// (the reference is fp32 end to end and logits are divided by temperature 0.1 before exp).
+#include "common.cuh"
+
+namespace nar {
+namespace gemm {
+
+constexpr int BM = 128;
+constexpr int BN = 128;
+constexpr int BK = 32;            // 32 fp32 = 128 B = one SWIZZLE_128B span
+constexpr int UMMA_K = 8;         // tf32: 32 B of K per instruction
+constexpr int TILE_A_BYTES = BM * BK * 4;
+constexpr int TILE_B_BYTES = BN * BK * 4;
+constexpr int NUM_THREADS = 256;
+constexpr int TMEM_COLS = 128;
+
+template <bool SPLIT3> struct Cfg {
+  static constexpr int STAGE_BYTES = (SPLIT3 ? 2 : 1) * (TILE_A_BYTES + TILE_B_BYTES);
+  static constexpr int STAGES = SPLIT3 ? 3 : 6;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;   // tiles + barriers + align slack
+};
+
+struct Params {
+  int64_t M, N, K;
+  float* D; int64_t ldd;
+  const float* bias;
+  const float* aux; int64_t ld_aux;
+  int act, dact, accumulate;
+  int k_tiles_per_split;
+  int n_tiles;                 // blockIdx.x = m_blk * n_tiles + n_blk (N fastest: CTAs sharing an A tile run together)
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  // bounded spin: a protocol bug traps (launch error) instead of hanging the GPU
+  for (uint32_t it = 0; it < (1u << 26); ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+//   [0,14) start>>4  [16,30) LBO>>4  [32,46) SBO>>4  [46,48) version=1  [61,64) layout (2 = SWIZZLE_128B)
+// K-major tile  (rows x 128 B, 8-row atoms 1024 B apart):            LBO unused (1), SBO = 1024
+// MN-major tile (k rows x 128 B of MN, 32-wide MN chunks 4096 B apart): LBO = 4096,    SBO = 1024
+template <bool MN_MAJOR>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  const uint64_t lbo = MN_MAJOR ? (4096u >> 4) : 1u;
+  const uint64_t sbo = 1024u >> 4;
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// instruction descriptor (UMMA::InstrDescriptor): c_format F32 (1<<4), a/b format TF32 (2<<7, 2<<10),
+// a_major bit 15, b_major bit 16 (1 = MN-major), N>>3 at [17,23), M>>4 at [24,29)
+template <bool A_MN, bool B_MN>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ float tf32_lo(float x) {
+  return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+}
+
+// ---------------------------------------------------------------- kernel
+template <bool A_MN, bool B_MN, bool SPLIT3>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+  using C = Cfg<SPLIT3>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* tiles = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C::STAGES;
+  uint64_t* xf = bars + 2 * C::STAGES;
+  uint64_t* tmem_full = bars + 3 * C::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * C::STAGES + 1);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_blk = blockIdx.x % p.n_tiles, m_blk = blockIdx.x / p.n_tiles;
+  const int k_tiles_total = (int)((p.K + BK - 1) / BK);
+  const int kt0 = blockIdx.y * p.k_tiles_per_split;
+  const int kt1 = min(kt0 + p.k_tiles_per_split, k_tiles_total);
+  const int num_kt = kt1 - kt0;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+      mbar_init(&xf[s], 128);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp_idx == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      for (int kt = 0; kt < num_kt; ++kt) {
+        const int s = kt % C::STAGES;
+        const uint32_t ph = (uint32_t)(kt / C::STAGES) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        mbar_expect_tx(&full[s], TILE_A_BYTES + TILE_B_BYTES);
+        const int k_elem = (kt0 + kt) * BK;
+        const uint32_t a_dst = smem_u32(tiles + s * C::STAGE_BYTES);
+        const uint32_t b_dst = a_dst + TILE_A_BYTES;
+        if (!A_MN) {
+          tma_load_2d(a_dst, &tmap_a, &full[s], k_elem, m_blk * BM);
+        } else {
+#pragma unroll
+          for (int i = 0; i < BM / 32; ++i) tma_load_2d(a_dst + i * 4096, &tmap_a, &full[s], m_blk * BM + i * 32, k_elem);
+        }
+        if (!B_MN) {
+          tma_load_2d(b_dst, &tmap_b, &full[s], k_elem, n_blk * BN);
+        } else {
+#pragma unroll
+          for (int i = 0; i < BN / 32; ++i) tma_load_2d(b_dst + i * 4096, &tmap_b, &full[s], n_blk * BN + i * 32, k_elem);
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc<A_MN, B_MN>();
+      constexpr uint32_t a_kstep = A_MN ? 1024u : (uint32_t)(UMMA_K * 4);
+      constexpr uint32_t b_kstep = B_MN ? 1024u : (uint32_t)(UMMA_K * 4);
+      for (int kt = 0; kt < num_kt; ++kt) {
+        const int s = kt % C::STAGES;
+        const uint32_t ph = (uint32_t)(kt / C::STAGES) & 1u;
+        mbar_wait(SPLIT3 ? &xf[s] : &full[s], ph);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(tiles + s * C::STAGE_BYTES);
+        const uint32_t b_hi = a_hi + TILE_A_BYTES;
+        const uint32_t a_lo = b_hi + TILE_B_BYTES;
+        const uint32_t b_lo = a_lo + TILE_A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t da = make_smem_desc<A_MN>(a_hi + k * a_kstep);
+          const uint64_t db = make_smem_desc<B_MN>(b_hi + k * b_kstep);
+          if (SPLIT3) {
+            const uint64_t dal = make_smem_desc<A_MN>(a_lo + k * a_kstep);
+            const uint64_t dbl = make_smem_desc<B_MN>(b_lo + k * b_kstep);
+            umma_tf32(tmem_base, dal, db, idesc, (kt > 0 || k > 0) ? 1u : 0u);   // small terms first
+            umma_tf32(tmem_base, da, dbl, idesc, 1u);
+            umma_tf32(tmem_base, da, db, idesc, 1u);
+          } else {
+            umma_tf32(tmem_base, da, db, idesc, (kt > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty[s]);     // frees the smem slot when these MMAs retire
+      }
+      umma_commit(tmem_full);       // accumulator complete
+    }
+  } else if (warp_idx >= 4) {
+    const int ew = warp_idx - 4;            // TMEM lane quadrant == warp_idx % 4
+    if (SPLIT3) {
+      // ===== operand split: lo = x - trunc_tf32(x) for the A and B tiles of each stage =====
+      const int te = threadIdx.x - 128;
+      for (int kt = 0; kt < num_kt; ++kt) {
+        const int s = kt % C::STAGES;
+        const uint32_t ph = (uint32_t)(kt / C::STAGES) & 1u;
+        mbar_wait(&full[s], ph);
+        const float4* hi = reinterpret_cast<const float4*>(tiles + s * C::STAGE_BYTES);
+        float4* lo = reinterpret_cast<float4*>(tiles + s * C::STAGE_BYTES + TILE_A_BYTES + TILE_B_BYTES);
+#pragma unroll 4
+        for (int i = te; i < (TILE_A_BYTES + TILE_B_BYTES) / 16; i += 128) {
+          float4 v = hi[i];
+          v.x = tf32_lo(v.x); v.y = tf32_lo(v.y); v.z = tf32_lo(v.z); v.w = tf32_lo(v.w);
+          lo[i] = v;
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&xf[s]);
+      }
+    }
+    // ===== epilogue =====
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int64_t row = (int64_t)m_blk * BM + ew * 32 + lane;
+    const bool row_ok = row < p.M;
+    for (int c = 0; c < BN; c += 32) {
+      const int64_t col0 = (int64_t)n_blk * BN + c;
+      if (col0 >= p.N) break;               // warp-uniform
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c, r);
+      if (!row_ok) continue;
+      float* drow = p.D + row * p.ldd + col0;
+      const float* arow = p.dact ? (p.aux + row * p.ld_aux + col0) : nullptr;
+      if (col0 + 32 <= p.N) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          if (p.bias) {
+            const float4 b = *reinterpret_cast<const float4*>(p.bias + col0 + j);
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+          }
+          if (p.act) { v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act); v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act); }
+          if (p.dact) {
+            const float4 a = *reinterpret_cast<const float4*>(arow + j);
+            v.x *= act_grad_from_output(a.x, p.dact); v.y *= act_grad_from_output(a.y, p.dact);
+            v.z *= act_grad_from_output(a.z, p.dact); v.w *= act_grad_from_output(a.w, p.dact);
+          }
+          if (p.accumulate) {
+            atomicAdd(drow + j, v.x); atomicAdd(drow + j + 1, v.y); atomicAdd(drow + j + 2, v.z); atomicAdd(drow + j + 3, v.w);
+          } else {
+            *reinterpret_cast<float4*>(drow + j) = v;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (col0 + j < p.N) {
+            float v = __uint_as_float(r[j]);
+            if (p.bias) v += p.bias[col0 + j];
+            v = apply_act(v, p.act);
+            if (p.dact) v *= act_grad_from_output(arow[j], p.dact);
+            if (p.accumulate) atomicAdd(drow + j, v); else drow[j] = v;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// operand with logical shape [mn, k]; kmajor: ptr[mn*ld + k] else ptr[k*ld + mn]
+static int make_operand_map(const nar_ctx* ctx, CUtensorMap* map, const float* ptr, int64_t mn, int64_t k, int64_t ld, bool kmajor) {
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0 || (ld & 3) != 0 || ld <= 0) return NAR_ERR_INVALID;
+  cuuint64_t dims[2]; cuuint64_t strides[1]; cuuint32_t box[2]; cuuint32_t estr[2] = {1, 1};
+  if (kmajor) { dims[0] = (cuuint64_t)k; dims[1] = (cuuint64_t)mn; box[0] = BK; box[1] = BM; }
+  else        { dims[0] = (cuuint64_t)mn; dims[1] = (cuuint64_t)k; box[0] = 32; box[1] = BK; }
+  strides[0] = (cuuint64_t)ld * 4;
+  CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
+      map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? NAR_OK : NAR_ERR_INVALID;
+}
+
+template <bool A_MN, bool B_MN, bool SPLIT3>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, dim3 grid, cudaStream_t st) {
+  auto kern = gemm_tf32_kernel<A_MN, B_MN, SPLIT3>;
+  static bool attr_set = false;     // per instantiation
+  if (!attr_set) {
+    NAR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<SPLIT3>::SMEM_BYTES));
+    attr_set = true;
+  }
+  kern<<<grid, NUM_THREADS, Cfg<SPLIT3>::SMEM_BYTES, st>>>(ta, tb, p);
+  NAR_LAUNCH_CHECK();
+  return NAR_OK;
+}
+
+}  // namespace gemm
+}  // namespace nar
+
+extern "C" int nar_gemm_tf32(nar_ctx* ctx, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, int a_kmajor,
+                             const float* B, int64_t ldb, int b_kmajor, float* D, int64_t ldd,
+                             const nar_gemm_epilogue* epi, void* stream) {
+  using namespace nar::gemm;
+  if (!ctx || !ctx->encode_tiled) return NAR_ERR_NO_DEVICE;
+  if (!A || !B || !D || !epi) return NAR_ERR_INVALID;
+  if (M <= 0 || N <= 0 || K <= 0) return NAR_OK;     // empty problem: nothing to do
+  if ((ldd & 3) != 0 || (reinterpret_cast<uintptr_t>(D) & 15u) != 0) return NAR_ERR_INVALID;
+  if (epi->bias && (reinterpret_cast<uintptr_t>(epi->bias) & 15u) != 0) return NAR_ERR_INVALID;
+  if (epi->dact && (!epi->aux || (epi->ld_aux & 3) != 0 || (reinterpret_cast<uintptr_t>(epi->aux) & 15u) != 0)) return NAR_ERR_INVALID;
+  if (epi->precision != 1 && epi->precision != 3) return NAR_ERR_INVALID;
+  const int k_tiles = (int)((K + BK - 1) / BK);
+  int split = epi->split_k < 1 ? 1 : epi->split_k;
+  if (split > k_tiles) split = k_tiles;
+  if (split > 1 && !epi->accumulate) return NAR_ERR_INVALID;
+  int per = (k_tiles + split - 1) / split;
+  split = (k_tiles + per - 1) / per;          // no empty splits
+  CUtensorMap ta, tb;
+  int rc = make_operand_map(ctx, &ta, A, M, K, lda, a_kmajor != 0);
+  if (rc) return rc;
+  rc = make_operand_map(ctx, &tb, B, N, K, ldb, b_kmajor != 0);
+  if (rc) return rc;
+  Params p;
+  p.M = M; p.N = N; p.K = K; p.D = D; p.ldd = ldd; p.bias = epi->bias; p.aux = epi->aux; p.ld_aux = epi->ld_aux;
+  p.act = epi->act; p.dact = epi->dact; p.accumulate = epi->accumulate; p.k_tiles_per_split = per;
+  const int64_t n_tiles = (N + BN - 1) / BN, m_tiles = (M + BM - 1) / BM;
+  if (n_tiles * m_tiles > 0x7fffffffLL) return NAR_ERR_UNSUPPORTED;
+  p.n_tiles = (int)n_tiles;
+  dim3 grid((unsigned)(n_tiles * m_tiles), (unsigned)split, 1);
+  cudaStream_t st = as_stream(stream);
+  const bool amn = !a_kmajor, bmn = !b_kmajor, s3 = epi->precision == 3;
+#define NAR_GEMM_CASE(a, b, s) if (amn == a && bmn == b && s3 == s) return launch<a, b, s>(ta, tb, p, grid, st);
+  NAR_GEMM_CASE(false, false, false) NAR_GEMM_CASE(false, false, true)
+  NAR_GEMM_CASE(false, true, false)  NAR_GEMM_CASE(false, true, true)
+  NAR_GEMM_CASE(true, false, false)  NAR_GEMM_CASE(true, false, true)
+  NAR_GEMM_CASE(true, true, false)   NAR_GEMM_CASE(true, true, true)
+#undef NAR_GEMM_CASE
+  return NAR_ERR_INVALID;
+}

@@ -1,0 +1,174 @@
+// Context + small HBM-bound helpers: TF-flavoured Adam, column sums (bias grads), l2 loss,
+// transpose (Wh^T for BPTT), activation backward.
+#include "common.cuh"
+
+namespace nar {
+namespace misc {
+
+// tf.train.AdamOptimizer (nar_model.py:708-722): lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed on the host
+// in double; w -= lr_t * m / (sqrt(v) + eps).  Elements [0, reg_end) carry an l2_regularizer:
+// their gradient gets + reg_l2 * w (d/dw of reg_l2 * sum(w^2)/2).
+__global__ void __launch_bounds__(256)
+adam_tf_kernel(float4* __restrict__ w, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
+               int64_t n4, int64_t reg_end4, float reg_l2, float lr_t, float b1, float b2, float eps) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 wi = w[i], gi = g[i], mi = m[i], vi = v[i];
+    const float r = i < reg_end4 ? reg_l2 : 0.f;
+#define NAR_ADAM1(c)                                              \
+    { const float gg = fmaf(r, wi.c, gi.c);                       \
+      mi.c = b1 * mi.c + (1.f - b1) * gg;                         \
+      vi.c = b2 * vi.c + (1.f - b2) * gg * gg;                    \
+      wi.c -= lr_t * mi.c / (sqrtf(vi.c) + eps); }
+    NAR_ADAM1(x) NAR_ADAM1(y) NAR_ADAM1(z) NAR_ADAM1(w)
+#undef NAR_ADAM1
+    w[i] = wi; m[i] = mi; v[i] = vi;
+  }
+}
+
+// out[c] += sum_r x[r,c] ; CTA = 256 columns x 64-row slab
+__global__ void __launch_bounds__(256)
+colsum_add_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld, float* __restrict__ out) {
+  const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.y * 64, r1 = min(rows, r0 + 64);
+  if (c >= cols) return;
+  float acc = 0.f;
+  for (int64_t r = r0; r < r1; ++r) acc += x[r * ld + c];
+  atomicAdd(out + c, acc);
+}
+
+__global__ void __launch_bounds__(256)
+l2_loss_add_kernel(const float* __restrict__ x, int64_t n, float scale, float* __restrict__ out) {
+  __shared__ float sh[8];
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    acc = fmaf(v, v, acc);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sh[i];
+    atomicAdd(out, scale * 0.5f * t);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, int64_t n, int act, float* __restrict__ dx) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dx[i] = dy[i] * act_grad_from_output(y[i], act);
+}
+
+__global__ void __launch_bounds__(256)
+transpose_kernel(const float* __restrict__ src, int64_t rows, int64_t cols, int64_t ld_src, float* __restrict__ dst, int64_t ld_dst) {
+  __shared__ float tile[32][33];
+  const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < rows && c < cols) ? src[r * ld_src + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t c = c0 + i, r = r0 + tx;       // dst[c, r]
+    if (c < cols && r < rows) dst[c * ld_dst + r] = tile[tx][i];
+  }
+}
+
+static unsigned grid_for(int64_t n, int per_block) {
+  int64_t g = (n + per_block - 1) / per_block;
+  const int64_t cap = 148 * 8;
+  return (unsigned)(g > cap ? cap : (g < 1 ? 1 : g));
+}
+
+}  // namespace misc
+}  // namespace nar
+
+// ------------------------------------------------------------------ context
+extern "C" int nar_abi_version(void) { return NAR_ABI_VERSION; }
+
+extern "C" const char* nar_status_string(int status) {
+  switch (status) {
+    case NAR_OK: return "ok";
+    case NAR_ERR_INVALID: return "invalid argument";
+    case NAR_ERR_UNSUPPORTED: return "unsupported";
+    case NAR_ERR_NO_DEVICE: return "no sm_100 CUDA device / driver entry point";
+    case NAR_ERR_WORKSPACE: return "workspace too small";
+  }
+  if (status > 0) return cudaGetErrorString((cudaError_t)status);
+  return "unknown";
+}
+
+extern "C" int nar_ctx_create(int device, nar_ctx** out) {
+  if (!out) return NAR_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return NAR_ERR_NO_DEVICE;
+  cudaDeviceProp prop;
+  NAR_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return NAR_ERR_NO_DEVICE;        // sm_100a code only
+  NAR_CHECK_CUDA(cudaSetDevice(device));
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return NAR_ERR_NO_DEVICE;
+  nar_ctx* c = new nar_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->encode_tiled = fn;
+  *out = c;
+  return NAR_OK;
+}
+
+extern "C" int nar_ctx_destroy(nar_ctx* ctx) {
+  delete ctx;
+  return NAR_OK;
+}
+
+// ------------------------------------------------------------------ helpers
+extern "C" int nar_adam_tf(float* params, const float* grads, float* m, float* v, int64_t n, int64_t reg_end, float reg_l2,
+                           float lr, float beta1, float beta2, float eps, int64_t step, void* stream) {
+  if (!params || !grads || !m || !v || (n & 3) || (reg_end & 3) || step < 1) return NAR_ERR_INVALID;
+  if (n == 0) return NAR_OK;
+  const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
+  nar::misc::adam_tf_kernel<<<nar::misc::grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<float4*>(params), reinterpret_cast<const float4*>(grads), reinterpret_cast<float4*>(m),
+      reinterpret_cast<float4*>(v), n / 4, reg_end / 4, reg_l2, (float)lr_t, beta1, beta2, eps);
+  NAR_LAUNCH_CHECK();
+  return NAR_OK;
+}
+
+extern "C" int nar_colsum_add(const float* x, int64_t rows, int64_t cols, int64_t ld, float* out, void* stream) {
+  if (!x || !out) return NAR_ERR_INVALID;
+  if (rows <= 0 || cols <= 0) return NAR_OK;
+  dim3 grid((unsigned)((cols + 255) / 256), (unsigned)((rows + 63) / 64));
+  if (grid.y > 65535u) return NAR_ERR_UNSUPPORTED;
+  nar::misc::colsum_add_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, rows, cols, ld, out);
+  NAR_LAUNCH_CHECK();
+  return NAR_OK;
+}
+
+extern "C" int nar_l2_loss_add(const float* x, int64_t n, float scale, float* out, void* stream) {
+  if (!x || !out) return NAR_ERR_INVALID;
+  if (n <= 0) return NAR_OK;
+  nar::misc::l2_loss_add_kernel<<<nar::misc::grid_for(n, 1024), 256, 0, as_stream(stream)>>>(x, n, scale, out);
+  NAR_LAUNCH_CHECK();
+  return NAR_OK;
+}
+
+extern "C" int nar_act_bwd(const float* dy, const float* y, int64_t n, int act, float* dx, void* stream) {
+  if (!dy || !y || !dx) return NAR_ERR_INVALID;
+  if (n <= 0) return NAR_OK;
+  nar::misc::act_bwd_kernel<<<nar::misc::grid_for(n, 1024), 256, 0, as_stream(stream)>>>(dy, y, n, act, dx);
+  NAR_LAUNCH_CHECK();
+  return NAR_OK;
+}
+
+extern "C" int nar_transpose_f32(const float* src, int64_t rows, int64_t cols, int64_t ld_src, float* dst, int64_t ld_dst, void* stream) {
+  if (!src || !dst) return NAR_ERR_INVALID;
+  if (rows <= 0 || cols <= 0) return NAR_OK;
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+  nar::misc::transpose_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, rows, cols, ld_src, dst, ld_dst);
+  NAR_LAUNCH_CHECK();
+  return NAR_OK;
+}

@@ -1,0 +1,155 @@
+"""torch-tensor wrappers over the C ABI (include/nar_b200.h).  torch is only the container:
+allocation, streams, pointers.  Every function launches on torch's current CUDA stream."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ACT_LEAKY, ACT_NONE, ACT_TANH, Context, FeaturePlanC, GemmEpilogue, NarError, check
+
+_ctx: dict = {}
+
+
+def context(device: Optional[int] = None) -> Context:
+    if device is None:
+        device = torch.cuda.current_device()
+    if device not in _ctx:
+        _ctx[device] = Context(device)
+    return _ctx[device]
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _chk_f32(*ts):
+    for t in ts:
+        if t is not None:
+            assert t.is_cuda and t.dtype == torch.float32, (t.device, t.dtype)
+
+
+def gemm(A: torch.Tensor, B: torch.Tensor, D: torch.Tensor, M: int, N: int, K: int, *, a_kmajor=True, b_kmajor=True,
+         lda=None, ldb=None, ldd=None, bias=None, act=ACT_NONE, dact=ACT_NONE, aux=None, ld_aux=None,
+         accumulate=False, split_k=1, precision=3):
+    """D[M,N] = epilogue(sum_k A(m,k) B(n,k)); see nar_gemm_tf32."""
+    _chk_f32(A, B, D, bias, aux)
+    lda = A.stride(0) if lda is None else lda
+    ldb = B.stride(0) if ldb is None else ldb
+    ldd = D.stride(0) if ldd is None else ldd
+    epi = GemmEpilogue(_p(bias), act, dact, _p(aux), (aux.stride(0) if (aux is not None and ld_aux is None) else (ld_aux or 0)),
+                       1 if accumulate else 0, int(split_k), int(precision))
+    ctx = context()
+    check(ctx.lib.nar_gemm_tf32(ctx.handle, M, N, K, _p(A), lda, 1 if a_kmajor else 0, _p(B), ldb, 1 if b_kmajor else 0,
+                                _p(D), ldd, C.byref(epi), _stream()), 'nar_gemm_tf32')
+
+
+def gather_rows(table: torch.Tensor, ids: torch.Tensor, out: torch.Tensor, width: int):
+    _chk_f32(table, out)
+    assert ids.dtype == torch.int64
+    lib = _lib.load()
+    check(lib.nar_gather_rows_f32(_p(table), table.shape[0], table.stride(0), width, _p(ids), ids.numel(), _p(out),
+                                  out.stride(0), _stream()), 'nar_gather_rows_f32')
+
+
+def scatter_add_rows(table: torch.Tensor, ids: torch.Tensor, src: torch.Tensor, width: int):
+    _chk_f32(table, src)
+    lib = _lib.load()
+    check(lib.nar_scatter_add_rows_f32(_p(table), table.shape[0], table.stride(0), width, _p(ids), ids.numel(), _p(src),
+                                       src.stride(0), _stream()), 'nar_scatter_add_rows_f32')
+
+
+def gather_features(plan: FeaturePlanC, row_pos, row_item, n_rows, n_input, n_cand, event_ts, max_ts, out):
+    ctx = context()
+    check(ctx.lib.nar_gather_features(ctx.handle, C.byref(plan), _p(row_pos), _p(row_item), n_rows, n_input, n_cand,
+                                      _p(event_ts), _p(max_ts), _p(out), _stream()), 'nar_gather_features')
+
+
+def gather_features_bwd(plan: FeaturePlanC, row_pos, row_item, n_rows, n_input, n_cand, event_ts, max_ts, d_out, d_gamma, d_beta):
+    ctx = context()
+    check(ctx.lib.nar_gather_features_bwd(ctx.handle, C.byref(plan), _p(row_pos), _p(row_item), n_rows, n_input, n_cand,
+                                          _p(event_ts), _p(max_ts), _p(d_out), _p(d_gamma), _p(d_beta), _stream()),
+          'nar_gather_features_bwd')
+
+
+def feature_stats(buffer, n_norm, created_at_ts, pop_norm, max_ts, log_base_rec, log_base_nov, row_pos, row_item,
+                  n_rows, n_input, n_cand, event_ts, stats):
+    ctx = context()
+    check(ctx.lib.nar_feature_stats(ctx.handle, _p(buffer), buffer.numel(), n_norm, _p(created_at_ts), _p(pop_norm),
+                                    _p(max_ts), log_base_rec, log_base_nov, _p(row_pos), _p(row_item), n_rows, n_input,
+                                    n_cand, _p(event_ts), _p(stats), _stream()), 'nar_feature_stats')
+
+
+def ugrnn_fwd(gx, Wh, sess_off, B, Hp, h_out, gate, cand):
+    ctx = context()
+    check(ctx.lib.nar_ugrnn_fwd(ctx.handle, _p(gx), _p(Wh), _p(sess_off), B, Hp, _p(h_out), _p(gate), _p(cand), _stream()),
+          'nar_ugrnn_fwd')
+
+
+def ugrnn_bwd(d_hout, h_out, gate, cand, WhT, sess_off, B, Hp, d_gx, h_prev):
+    ctx = context()
+    check(ctx.lib.nar_ugrnn_bwd(ctx.handle, _p(d_hout), _p(h_out), _p(gate), _p(cand), _p(WhT), _p(sess_off), B, Hp,
+                                _p(d_gx), _p(h_prev), _stream()), 'nar_ugrnn_bwd')
+
+
+def sample_negatives_workspace(Bg, T1, buf_len, K) -> int:
+    lib = _lib.load()
+    n = C.c_int64(0)
+    check(lib.nar_sample_negatives_workspace(Bg, T1, buf_len, K, C.byref(n)), 'nar_sample_negatives_workspace')
+    return int(n.value)
+
+
+def sample_negatives(all_items_global, sess0, B, buffer, K, n_from_buffer, seed, step, out, workspace):
+    ctx = context()
+    Bg, T1 = all_items_global.shape
+    check(ctx.lib.nar_sample_negatives(ctx.handle, _p(all_items_global), Bg, T1, sess0, B, _p(buffer), buffer.numel(), K,
+                                       n_from_buffer, C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), C.c_uint32(step & 0xFFFFFFFF),
+                                       _p(out), _p(workspace), workspace.numel() * workspace.element_size(), _stream()),
+          'nar_sample_negatives')
+
+
+def mul_pred(cand, pred, n_pos, n_cand, Cdim, prod):
+    check(_lib.load().nar_mul_pred(_p(cand), _p(pred), n_pos, n_cand, Cdim, _p(prod), _stream()), 'nar_mul_pred')
+
+
+def mul_pred_bwd(d_prod, cand, pred, n_pos, n_cand, Cdim, d_cand, d_pred):
+    check(_lib.load().nar_mul_pred_bwd(_p(d_prod), _p(cand), _p(pred), n_pos, n_cand, Cdim, _p(d_cand), _p(d_pred), _stream()),
+          'nar_mul_pred_bwd')
+
+
+def score_softmax_ce(z3, ld_z, width, m4, ld_m4, c4, n_pos, n_cand, inv_temp, inv_count, logits, loss_sum, d_z3, d_m4, d_c4):
+    check(_lib.load().nar_score_softmax_ce(_p(z3), ld_z, width, _p(m4), ld_m4, _p(c4), n_pos, n_cand, inv_temp, inv_count,
+                                           _p(logits), _p(loss_sum), _p(d_z3), _p(d_m4), _p(d_c4), _stream()),
+          'nar_score_softmax_ce')
+
+
+def cosine_softmax_ce(cand, pred, n_pos, n_cand, Cdim, inv_temp, inv_count, logits, loss_sum, d_cand, d_pred):
+    check(_lib.load().nar_cosine_softmax_ce(_p(cand), _p(pred), n_pos, n_cand, Cdim, inv_temp, inv_count, _p(logits),
+                                            _p(loss_sum), _p(d_cand), _p(d_pred), _stream()), 'nar_cosine_softmax_ce')
+
+
+def colsum_add(x, rows, cols, ld, out):
+    check(_lib.load().nar_colsum_add(_p(x), rows, cols, ld, _p(out), _stream()), 'nar_colsum_add')
+
+
+def act_bwd(dy, y, n, act, dx):
+    check(_lib.load().nar_act_bwd(_p(dy), _p(y), n, act, _p(dx), _stream()), 'nar_act_bwd')
+
+
+def l2_loss_add(x, n, scale, out):
+    check(_lib.load().nar_l2_loss_add(_p(x), n, scale, _p(out), _stream()), 'nar_l2_loss_add')
+
+
+def transpose(src, rows, cols, ld_src, dst, ld_dst):
+    check(_lib.load().nar_transpose_f32(_p(src), rows, cols, ld_src, _p(dst), ld_dst, _stream()), 'nar_transpose_f32')
+
+
+def adam_tf(params, grads, m, v, n, reg_end, reg_l2, lr, step, beta1=0.9, beta2=0.999, eps=1e-8):
+    check(_lib.load().nar_adam_tf(_p(params), _p(grads), _p(m), _p(v), n, reg_end, reg_l2, lr, beta1, beta2, eps, step,
+                                  _stream()), 'nar_adam_tf')

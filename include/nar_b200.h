@@ -1,0 +1,205 @@
+/*
+ * nar_b200.h - C ABI of the B200-native NAR (CHAMELEON next-article recommendation)
+ * training hot path.  libnar_b200.so exports exactly these symbols.
+ *
+ * The reference (gabrielspmoreira/chameleon_recsys @ 2e50af5) has NO native / FFI layer:
+ * its boundary is the TF-Estimator Python contract (nar_module/nar/nar_trainer_gcom.py:234-332
+ * model_fn, nar_module/nar/datasets.py:166-179 input_fn) and every "kernel" is a TensorFlow
+ * 1.12 library op.  Each entry point below therefore cites the reference op group it
+ * replaces (file:line of the TF call site) instead of a pre-existing FFI declaration.
+ *
+ * Conventions: extern "C"; plain pointers and sizes; every pointer is a DEVICE pointer
+ * unless it says "host"; the caller owns every buffer; `stream` is a cudaStream_t passed
+ * as void*; functions return 0 on success, a negative nar_status, or a positive
+ * cudaError_t; nothing throws; no hidden global state beyond the opaque nar_ctx.
+ * There is no CPU fallback anywhere: without a CUDA device every call fails.
+ */
+#ifndef NAR_B200_H
+#define NAR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NAR_ABI_VERSION 1
+
+typedef enum {
+  NAR_OK = 0,
+  NAR_ERR_INVALID = -1,        /* bad argument (null pointer, misaligned ld, size limit) */
+  NAR_ERR_UNSUPPORTED = -2,    /* valid request the library does not implement */
+  NAR_ERR_NO_DEVICE = -3,      /* no sm_100 device / driver entry point missing */
+  NAR_ERR_WORKSPACE = -4       /* workspace too small */
+} nar_status;
+
+typedef struct nar_ctx nar_ctx;
+
+/* ---- context ------------------------------------------------------------------------- */
+int  nar_abi_version(void);
+const char* nar_status_string(int status);
+int  nar_ctx_create(int device, nar_ctx** out);
+int  nar_ctx_destroy(nar_ctx* ctx);
+
+/* ---- feature-row gather  (replaces tf.nn.embedding_lookup nar_model.py:948 (ACR, frozen),
+ *      :918 (trainable item embedding), tf.gather :929/:1067/:1095/:1138, tf.one_hot :734,
+ *      small embedding_lookup :741, recency/novelty normalisation :996-1193, the concat
+ *      :332/:992 and scale_center_features :905).  One output row per (position, item)
+ *      pair; written straight into the GEMM A operand.                                     */
+typedef enum {
+  NAR_SEG_CTX_OHE = 0, NAR_SEG_CTX_EMBED = 1, NAR_SEG_CTX_NUM = 2, NAR_SEG_CTX_ZERO = 3,
+  NAR_SEG_META_OHE = 4, NAR_SEG_META_EMBED = 5, NAR_SEG_META_NUM = 6,
+  NAR_SEG_ACR = 7, NAR_SEG_ITEM_EMB = 8, NAR_SEG_RECENCY = 9, NAR_SEG_NOVELTY = 10
+} nar_seg_kind;
+
+typedef struct {
+  int32_t kind;        /* nar_seg_kind */
+  int32_t col;         /* first column in the output row */
+  int32_t width;       /* columns written */
+  int32_t card;        /* categorical cardinality (OHE / EMBED) */
+  int32_t src;         /* index into ctx_int / ctx_float / meta pointer arrays */
+  int32_t ld;          /* leading dimension of `table` (floats) */
+  const float* table;  /* embedding table (EMBED, ACR, ITEM_EMB) */
+  float* grad;         /* gradient table for trainable embeddings (backward only) */
+} nar_segment;
+
+#define NAR_MAX_SEGMENTS 24
+#define NAR_MAX_SRC 16
+
+typedef struct {
+  int32_t n_segments;
+  int32_t row_ld;                       /* floats per output row (Fp) */
+  nar_segment seg[NAR_MAX_SEGMENTS];
+  const int64_t* ctx_int[NAR_MAX_SRC];  /* [B*T] int64 context ids per feature */
+  const float*   ctx_float[NAR_MAX_SRC];/* [B*T] float context values per feature */
+  const int64_t* meta[NAR_MAX_SRC];     /* [V] int64 metadata per feature */
+  const int64_t* created_at_ts;         /* [V] int64 ms */
+  const float*   pop_norm;              /* [V] articles_recent_pop_norm */
+  const float*   gamma;                 /* [Fp] scale  (nar_model.py:891) */
+  const float*   beta;                  /* [Fp] centre (nar_model.py:895) */
+  const float*   stats;                 /* [3][8] normalisation stats (input / positive / negative rows), see nar_feature_stats */
+  float log_base_recency;               /* elapsed_days_smooth_log_base */
+  float log_base_novelty;               /* popularity_smooth_log_base */
+} nar_feature_plan;
+
+/* rows: row_pos[r] = flat index b*T+t of the position that owns row r (context features,
+ * reference timestamp), row_item[r] = article id, row_ts_kind: rows < n_input use
+ * event_timestamp[row_pos], the others use max_ts (nar_model.py:328,:343,:356).            */
+int nar_gather_features(nar_ctx* ctx, const nar_feature_plan* plan /*host*/,
+                        const int32_t* row_pos, const int64_t* row_item, int64_t n_rows, int64_t n_input,
+                        int64_t n_cand /* candidate rows come in groups of n_cand: positive first, then negatives */,
+                        const int64_t* event_timestamp /*[B*T]*/, const int64_t* max_ts /*[1]*/,
+                        float* out /*[n_rows,row_ld]*/, void* stream);
+
+/* backward of the same: d_gamma += sum_r dX*raw, d_beta += sum_r dX, trainable embedding
+ * grads += dX*gamma scattered by id (IndexedSlices scatter-add, nar_model.py:918/:741).     */
+int nar_gather_features_bwd(nar_ctx* ctx, const nar_feature_plan* plan /*host*/,
+                            const int32_t* row_pos, const int64_t* row_item, int64_t n_rows, int64_t n_input,
+                            int64_t n_cand, const int64_t* event_timestamp, const int64_t* max_ts,
+                            const float* d_out /*[n_rows,row_ld]*/, float* d_gamma, float* d_beta, void* stream);
+
+/* normalisation statistics of recency / novelty over the first n_norm nonzero buffer entries
+ * (nar_model.py:1062-1089, :1150-1193, :1011-1039).  stats[g][8], g = 0 input / 1 positive /
+ * 2 negative rows: {rec_mean, rec_std, rec_zmin, rec_zmax, nov_mean, nov_std, nov_zmin, nov_zmax};
+ * all three groups are equal unless the buffer is empty (first batch), where each group
+ * uses its own non-padded rows (the tf.cond at nar_model.py:1082 / :1179): pass the rows.    */
+int nar_feature_stats(nar_ctx* ctx, const int64_t* buffer, int64_t buf_len, int64_t n_norm,
+                      const int64_t* created_at_ts, const float* pop_norm, const int64_t* max_ts,
+                      float log_base_recency, float log_base_novelty,
+                      const int32_t* row_pos, const int64_t* row_item, int64_t n_rows, int64_t n_input,
+                      int64_t n_cand, const int64_t* event_timestamp,
+                      float* stats /*[24]*/, void* stream);
+
+/* plain row gather / scatter-add used by the parity tests and the roofline micro-benchmark
+ * (tf.nn.embedding_lookup nar_model.py:948 and its IndexedSlices gradient :918).           */
+int nar_gather_rows_f32(const float* table, int64_t n_table_rows, int64_t ld, int width,
+                        const int64_t* ids, int64_t n, float* out, int64_t ld_out, void* stream);
+int nar_scatter_add_rows_f32(float* table, int64_t n_table_rows, int64_t ld, int width,
+                             const int64_t* ids, int64_t n, const float* src, int64_t ld_src, void* stream);
+
+/* ---- dense contraction (replaces every tf.layers.Dense nar_model.py:375-473 and the
+ *      UGRNN input projection :1317 -> Eigen/MKL or cuBLAS sgemm in the reference).
+ *      D[M,N] = epilogue( sum_k A(m,k) * B(n,k) ), TMA-fed tcgen05.mma kind::tf32, fp32
+ *      accumulation in TMEM.  a_kmajor: A(m,k) = A[m*lda + k] else A[k*lda + m];
+ *      b_kmajor: B(n,k) = B[n*ldb + k] else B[k*ldb + n].                                  */
+typedef enum { NAR_ACT_NONE = 0, NAR_ACT_LEAKY_RELU = 1, NAR_ACT_TANH = 2 } nar_act;
+
+typedef struct {
+  const float* bias;      /* [N] added before the activation, or NULL */
+  int32_t act;            /* nar_act applied to acc+bias */
+  int32_t dact;           /* nar_act whose DERIVATIVE (evaluated from the forward OUTPUT aux) multiplies the result */
+  const float* aux;       /* [M,N] forward output of the layer being differentiated (dact != NONE) */
+  int64_t ld_aux;
+  int32_t accumulate;     /* 1: D += result with atomics (required when split_k > 1) */
+  int32_t split_k;        /* >=1 */
+  int32_t precision;      /* 1 = TF32, 3 = 3xTF32 (error-compensated, ~fp32 accuracy) */
+} nar_gemm_epilogue;
+
+int nar_gemm_tf32(nar_ctx* ctx, int64_t M, int64_t N, int64_t K,
+                  const float* A, int64_t lda, int a_kmajor,
+                  const float* B, int64_t ldb, int b_kmajor,
+                  float* D, int64_t ldd, const nar_gemm_epilogue* epi /*host*/, void* stream);
+
+/* ---- session RNN (replaces tf.contrib.rnn.UGRNNCell in MultiRNNCell / dynamic_rnn,
+ *      nar_model.py:1308-1342).  Rows are the valid positions only, grouped by session:
+ *      session b owns rows [sess_off[b], sess_off[b+1]).  gx = x*Wx + b for all rows
+ *      (nar_gemm_tf32), gate cols [0,Hp), candidate cols [Hp,2Hp).                          */
+int nar_ugrnn_fwd(nar_ctx* ctx, const float* gx /*[L,2Hp]*/, const float* Wh /*[Hp,2Hp]*/,
+                  const int32_t* sess_off /*[B+1]*/, int64_t B, int64_t Hp,
+                  float* h_out /*[L,Hp]*/, float* gate /*[L,Hp]*/, float* cand /*[L,Hp]*/, void* stream);
+int nar_ugrnn_bwd(nar_ctx* ctx, const float* d_hout /*[L,Hp]*/, const float* h_out, const float* gate,
+                  const float* cand, const float* WhT /*[2Hp,Hp]*/, const int32_t* sess_off, int64_t B,
+                  int64_t Hp, float* d_gx /*[L,2Hp]*/, float* h_prev /*[L,Hp]*/, void* stream);
+
+/* ---- negative sampler (replaces nar_model.py:1220-1304: tf.random_shuffle x(2+clicks),
+ *      tf.unique, unsorted_segment_min, tf.setdiff1d inside nested tf.map_fn).  RNG spec:
+ *      oracle/sampler_ref.py.  all_items_global [Bg,T1] builds the pool; negatives are
+ *      produced for local sessions [sess0, sess0+B).  out [B,T1-1,K] int64, zero padded.   */
+int nar_sample_negatives_workspace(int64_t Bg, int64_t T1, int64_t buf_len, int64_t K, int64_t* bytes /*host*/);
+int nar_sample_negatives(nar_ctx* ctx, const int64_t* all_items_global, int64_t Bg, int64_t T1,
+                         int64_t sess0, int64_t B, const int64_t* buffer, int64_t buf_len,
+                         int64_t K, int64_t n_from_buffer, uint64_t seed, uint32_t step,
+                         int64_t* out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- scorer + loss (replaces tf.multiply + matching_dense_layer_1..4 :478-500, softmax
+ *      :515, log :660, masked mean :664).                                                  */
+/* prod[r,:] = cand[r,:] * pred[r / n_cand,:]   (tf.multiply nar_model.py:478,:493)          */
+int nar_mul_pred(const float* cand, const float* pred, int64_t n_pos, int64_t n_cand, int64_t C,
+                 float* prod, void* stream);
+/* d_cand = d_prod*pred ; d_pred[l] = sum_j d_prod[l,j]*cand[l,j]                            */
+int nar_mul_pred_bwd(const float* d_prod, const float* cand, const float* pred, int64_t n_pos, int64_t n_cand,
+                     int64_t C, float* d_cand, float* d_pred, void* stream);
+/* last Dense(32->1) + /temperature + log-softmax over the 1+K candidates + masked mean CE,
+ * forward and backward in one pass.  z3 [n_pos*n_cand, ld_z] ; logits [n_pos,n_cand] ;
+ * loss_sum += sum_l -(logp[l,0]) * inv_count ; d_z3 = d(loss)/d(z3) (before leaky');
+ * d_m4[k] += ..., d_c4 += ...                                                              */
+int nar_score_softmax_ce(const float* z3, int64_t ld_z, int64_t width, const float* m4, int64_t ld_m4,
+                         const float* c4, int64_t n_pos, int64_t n_cand, float inv_temperature,
+                         float inv_count, float* logits, float* loss_sum, float* d_z3,
+                         float* d_m4, float* d_c4, void* stream);
+/* cosine mode (north_star wording; nar_model.py:437 commented l2-normalise): logits =
+ * <l2n(pred), l2n(cand)>/temperature fused with the same softmax-CE; writes d_cand, d_pred. */
+int nar_cosine_softmax_ce(const float* cand, const float* pred, int64_t n_pos, int64_t n_cand, int64_t C,
+                          float inv_temperature, float inv_count, float* logits, float* loss_sum,
+                          float* d_cand, float* d_pred, void* stream);
+
+/* ---- small helpers ------------------------------------------------------------------ */
+/* out[c] += sum_r x[r,c]   (bias gradients)                                                */
+int nar_colsum_add(const float* x, int64_t rows, int64_t cols, int64_t ld, float* out, void* stream);
+/* y = x * act'(aux) elementwise                                                            */
+int nar_act_bwd(const float* dy, const float* y, int64_t n, int act, float* dx, void* stream);
+/* out[0] += scale * sum(x^2) / 2  (l2_regularizer, nar_model.py:655)                       */
+int nar_l2_loss_add(const float* x, int64_t n, float scale, float* out, void* stream);
+int nar_transpose_f32(const float* src, int64_t rows, int64_t cols, int64_t ld_src, float* dst, int64_t ld_dst, void* stream);
+
+/* ---- optimiser (replaces tf.train.AdamOptimizer(lr,.9,.999,1e-8) nar_model.py:708-722;
+ *      TF form: lr_t = lr*sqrt(1-b2^t)/(1-b1^t); w -= lr_t*m/(sqrt(v)+eps); the gradient of
+ *      elements [0,reg_end) gets + reg_l2*w (l2_regularizer); grad is scaled by grad_scale
+ *      first (1/world after a sum-allreduce is NOT needed: losses are already global means) */
+int nar_adam_tf(float* params, const float* grads, float* m, float* v, int64_t n, int64_t reg_end,
+                float reg_l2, float lr, float beta1, float beta2, float eps, int64_t step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NAR_B200_H */

@@ -1,0 +1,301 @@
+"""TEST INFRASTRUCTURE - CPU restatement of the NAR training graph (torch-CPU, fp32 or fp64).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this module; the product path never does and fails loudly without its CUDA
+library.
+
+parity unpinned: the reference arithmetic lives in TensorFlow 1.12.3 (requirements.txt:5),
+which cannot be installed here (Python 3.12, no network), and the reference has no test,
+golden vector or fixture for logits / loss / gradients / Adam.  This
+file is therefore a line-by-line restatement of the graph, pinned only by (i) hand-derived
+known answers (tests/test_oracle_known_answers.py), (ii) finite-difference gradients,
+(iii) invariants from the code.  Every function cites the lines it follows.
+
+Restated: nar_module/nar/nar_model.py:219-245 (inputs/masks), :730-773 (get_features),
+:887-907 (scale/centre), :921-994 (item features), :996-1039 (normalisation), :1055-1089
+(recency), :1134-1193 (novelty), :374-405 (CAR), :1308-1342 + tf.contrib.rnn.UGRNNCell
+(RNN), :410-438 (FC), :444-517 (scorer + softmax), :639-704 (loss), :706-722 (Adam).
+It computes on every padded position like the reference does (masked only in the loss).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as Fn
+
+from chameleon_recsys_b200.hparams import ARTICLE_REQ_FEATURES, SESSION_REQ_SEQ_FEATURES, get_embedding_size
+
+LEAKY_ALPHA = 0.2       # tf.nn.leaky_relu default
+MS_PER_DAY = 1000.0 * 60.0 * 60.0 * 24.0
+
+
+def _t(x, dtype):
+    return torch.as_tensor(np.asarray(x)).to(dtype)
+
+
+class NarOracle:
+    """Pure function of (params, batch, state) -> loss / logits / grads; plus TF-Adam."""
+
+    def __init__(self, session_features_config, articles_features_config, internal_features_config,
+                 content_article_embeddings_matrix, articles_metadata, *, negative_samples,
+                 softmax_temperature=1.0, reg_weight_decay=0.0, recent_clicks_for_normalization=1000,
+                 elapsed_days_smooth_log_base=1.3, popularity_smooth_log_base=2.0, CAR_embedding_size=256,
+                 rnn_units=256, rnn_num_layers=1, max_cardinality_for_ohe=10, lr=1e-3,
+                 rnn_cell='ugrnn', ranking='mlp', dtype=torch.float32):
+        self.scfg = session_features_config
+        self.acfg = articles_features_config
+        self.icfg = internal_features_config
+        self.dtype = dtype
+        self.acr = _t(content_article_embeddings_matrix, torch.float32).to(dtype)
+        self.meta = {k: torch.as_tensor(np.asarray(v)) for k, v in articles_metadata.items()}
+        self.K = int(negative_samples)
+        self.tau = float(softmax_temperature)
+        self.reg = float(reg_weight_decay)
+        self.n_norm = int(recent_clicks_for_normalization)
+        self.rec_base = float(elapsed_days_smooth_log_base)
+        self.pop_base = float(popularity_smooth_log_base)
+        self.C = int(CAR_embedding_size)
+        self.H = int(rnn_units)
+        self.layers = int(rnn_num_layers)
+        self.max_ohe = int(max_cardinality_for_ohe)
+        self.lr = float(lr)
+        self.rnn_cell = rnn_cell
+        self.ranking = ranking
+        self.V = int(articles_features_config['article_id']['cardinality'])
+        self.adam_m: Dict[str, torch.Tensor] = {}
+        self.adam_v: Dict[str, torch.Tensor] = {}
+        self.step = 0
+
+    # ------------------------------------------------------------------ params
+    def set_params(self, logical: Dict[str, np.ndarray]):
+        self.params = {k: _t(v, torch.float32).to(self.dtype).clone().requires_grad_(True)
+                       for k, v in logical.items()}
+        self.adam_m = {k: torch.zeros_like(v) for k, v in self.params.items()}
+        self.adam_v = {k: torch.zeros_like(v) for k, v in self.params.items()}
+        self.step = 0
+
+    def get_params(self) -> Dict[str, np.ndarray]:
+        return {k: v.detach().cpu().numpy().copy() for k, v in self.params.items()}
+
+    def _p(self, name):
+        return self.params[name]
+
+    def regularised(self, name: str) -> bool:
+        """l2_regularizer is attached to Dense kernels, all embeddings, gamma, beta; not to
+        biases nor to the RNN (nar_model.py:378,386,414,426,450-471,740,894,898,917)."""
+        return (('/RNN/' not in name) and not name.endswith('/bias'))
+
+    # ------------------------------------------------------------------ features
+    def _log_base(self, x, base):
+        # nar_model.py:28-34
+        return torch.log(x) / math.log(base) if self.dtype == torch.float64 else \
+            torch.log(x) / torch.log(torch.tensor(base, dtype=self.dtype))
+
+    def get_features(self, inputs: Dict[str, torch.Tensor], features_config, features_to_ignore, scope: str):
+        """nar_model.py:730-773."""
+        feats = []
+        for fname, fc in features_config.items():
+            if fname in features_to_ignore:
+                continue
+            if fc['type'] == 'categorical':
+                size = fc['cardinality']
+                ids = inputs[fname].long()
+                if size <= self.max_ohe:
+                    oh = torch.zeros(ids.shape + (size,), dtype=self.dtype)
+                    ok = (ids >= 0) & (ids < size)
+                    oh.scatter_(-1, ids.clamp(0, size - 1).unsqueeze(-1), ok.to(self.dtype).unsqueeze(-1))
+                    feats.append(oh)
+                else:
+                    table = self._p(scope + '{}_cat_embedding/{}_embedding'.format(fname, fname))
+                    feats.append(table[ids])
+            elif fc['type'] == 'numerical':
+                feats.append(inputs[fname].to(self.dtype).unsqueeze(-1))
+            else:
+                raise Exception('Invalid feature type: {}'.format(fname))
+        if feats:
+            return torch.cat(feats, dim=-1)
+        return None
+
+    def _elapsed_days(self, creation_dates, reference_timestamps):
+        # nar_model.py:1055-1060 : int64 -> float32 cast BEFORE the subtraction
+        ref32 = reference_timestamps.to(torch.float32)
+        cre32 = creation_dates.to(torch.float32)
+        return torch.relu((ref32 - cre32) / torch.tensor(MS_PER_DAY, dtype=torch.float32)).to(self.dtype)
+
+    def _normalize_values(self, x, stats):
+        # nar_model.py:1011-1039 + :996-1009 ; tf.nn.moments = population variance
+        stats = stats.reshape(-1)
+        mean = stats.mean()
+        var = ((stats - mean) ** 2).mean()
+        std = torch.sqrt(var + 1e-24)
+        z = (x - mean) / std
+        zs = (stats - mean) / std
+        mn, mx = zs.min(), zs.max()
+        eps = 1e-24
+        scaled = (z - mn + eps) / torch.clamp(mx - mn, min=2 * eps)
+        return scaled * 2.0 - 1.0
+
+    def _buffer_last(self, buffer):
+        nz = buffer[buffer != 0]
+        return nz[:self.n_norm]
+
+    def item_features(self, item_ids, events_timestamp, max_ts, buffer, pop_norm):
+        """nar_model.py:921-994.  item_ids [...] i64; events_timestamp broadcastable i64 [..., 1]."""
+        feats = []
+        meta_vals = {f: self.meta[f][item_ids] for f in self.acfg if f not in ARTICLE_REQ_FEATURES}
+        if meta_vals:
+            feats.append(self.get_features(meta_vals, self.acfg, ARTICLE_REQ_FEATURES,
+                                           'main/user_items_contextual_features/item_features/features/'))
+        if self.icfg['article_content_embeddings']:
+            feats.append(self.acr[item_ids])
+        if self.icfg['item_clicked_embeddings']:
+            feats.append(self._p('main/user_items_contextual_features/item_features/item_cat_embedding/items_embedding')[item_ids])
+        nonpad = (item_ids != 0)
+        last = self._buffer_last(buffer)
+        if self.icfg['recency']:
+            created = self.meta['created_at_ts'][item_ids].unsqueeze(-1)
+            days = self._elapsed_days(created, events_timestamp)
+            sm = self._log_base(days + 1.0, self.rec_base)
+            if last.numel() == 0:
+                stats = sm[nonpad]                                   # tf.cond :1082 (first batch only)
+            else:
+                rdays = self._elapsed_days(self.meta['created_at_ts'][last], max_ts)
+                stats = self._log_base(rdays + 1.0, self.rec_base)
+            feats.append(self._normalize_values(sm, stats))
+        if self.icfg['novelty']:
+            nov = -self._log_base(pop_norm[item_ids].unsqueeze(-1), self.pop_base)
+            if last.numel() == 0:
+                stats = nov[nonpad]
+            else:
+                stats = -self._log_base(pop_norm[last], self.pop_base)
+            feats.append(self._normalize_values(nov, stats))
+        return torch.cat(feats, dim=-1)
+
+    # ------------------------------------------------------------------ layers
+    def _dense(self, x, name, act):
+        y = x @ self._p(name + '/kernel') + self._p(name + '/bias')
+        if act == 'leaky':
+            return Fn.leaky_relu(y, LEAKY_ALPHA)
+        if act == 'tanh':
+            return torch.tanh(y)
+        return y
+
+    def CAR(self, x):
+        # nar_model.py:374-403
+        return self._dense(self._dense(x, 'main/CAR/PreCAR_representation', 'leaky'),
+                           'main/CAR/CAR_representation', 'tanh')
+
+    def rnn(self, x, lengths):
+        """nar_model.py:1308-1342: MultiRNNCell of UGRNNCell inside dynamic_rnn(sequence_length)."""
+        B, T, _ = x.shape
+        H = self.H
+        states = [torch.zeros(B, H, dtype=self.dtype) for _ in range(self.layers)]
+        outs = []
+        for t in range(T):
+            inp = x[:, t]
+            new_states = []
+            for i in range(self.layers):
+                base = 'main/RNN/rnn/multi_rnn_cell/cell_{}/ugrnn_cell/'.format(i)
+                m = torch.cat([inp, states[i]], dim=1) @ self._p(base + 'kernel') + self._p(base + 'bias')
+                g_act, c_act = m[:, :H], m[:, H:]
+                c = torch.tanh(c_act)
+                g = torch.sigmoid(g_act + 1.0)                     # forget_bias = 1.0
+                h = g * states[i] + (1.0 - g) * c
+                new_states.append(h)
+                inp = h
+            alive = (t < lengths).to(self.dtype).unsqueeze(-1)
+            outs.append(inp * alive)                                # zero output past the length
+            states = [alive * ns + (1.0 - alive) * s for ns, s in zip(new_states, states)]
+        return torch.stack(outs, dim=1)
+
+    def scorer(self, cand, pred):
+        # nar_model.py:447-500 (cand [...,C] already multiplied outside for 'mlp')
+        if self.ranking == 'cosine':
+            return (Fn.normalize(cand, dim=-1) * Fn.normalize(pred, dim=-1)).sum(-1, keepdim=True)
+        z = cand * pred
+        base = 'main/recommendations_ranking/matching_dense_layer_'
+        z = self._dense(z, base + '1', 'leaky')
+        z = self._dense(z, base + '2', 'leaky')
+        z = self._dense(z, base + '3', 'leaky')
+        return self._dense(z, base + '4', None)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, features: Dict[str, np.ndarray], labels: Dict[str, np.ndarray], negatives: np.ndarray,
+                buffer: np.ndarray, pop_norm: np.ndarray, sum_mask_global: Optional[float] = None):
+        """-> dict with total_loss, xe_loss, reg_loss, logits [B,T,1+K] (already / temperature), mask, ..."""
+        item_clicked = torch.as_tensor(features['item_clicked']).long()
+        event_ts = torch.as_tensor(features['event_timestamp']).long().unsqueeze(-1)
+        lengths = torch.as_tensor(features['session_size']).long() - 1          # :227
+        B, T = item_clicked.shape
+        mask = (torch.arange(T)[None, :] < lengths[:, None])                     # :231
+        max_ts = event_ts.max()                                                  # :235
+        next_item = torch.as_tensor(labels['label_next_item']).long()
+        neg = torch.as_tensor(negatives).long()
+        buf = torch.as_tensor(np.asarray(buffer)).long()
+        pop = _t(np.asarray(pop_norm, dtype=np.float32), torch.float32).to(self.dtype)   # placeholder is float32
+
+        inputs = {k: torch.as_tensor(v) for k, v in features.items()}
+        ctx = self.get_features(inputs, self.scfg['sequence_features'], SESSION_REQ_SEQ_FEATURES,
+                                'main/user_items_contextual_features/features/')
+        if ctx is None:
+            ctx = torch.zeros(B, T, 1, dtype=self.dtype)                         # :325
+        gamma = self._p('main/user_items_contextual_features/input_features_center_scale/gamma_scale')
+        beta = self._p('main/user_items_contextual_features/input_features_center_scale/beta_center')
+
+        f_in = self.item_features(item_clicked, event_ts, max_ts, buf, pop)                        # :328
+        x_in = torch.cat([ctx, f_in], dim=2) * gamma + beta                                        # :332-333
+        f_pos = self.item_features(next_item, max_ts, max_ts, buf, pop)                            # :343
+        x_pos = torch.cat([ctx, f_pos], dim=2) * gamma + beta
+        f_neg = self.item_features(neg, max_ts, max_ts, buf, pop)                                  # :356
+        ctx_t = ctx.unsqueeze(2).expand(B, T, neg.shape[2], ctx.shape[-1])
+        x_neg = torch.cat([ctx_t, f_neg], dim=3) * gamma + beta                                    # :360-364
+
+        e_in, e_pos, e_neg = self.CAR(x_in), self.CAR(x_pos), self.CAR(x_neg)                      # :382-403
+        r = self.rnn(e_in, lengths)                                                                # :408
+        fc1 = self._dense(r, 'main/session_representation/FC1', 'leaky')                           # :411
+        pred = self._dense(fc1, 'main/session_representation/FC2', 'tanh')                         # :423-438
+        s_pos = self.scorer(e_pos, pred)                                                           # :478-485
+        s_neg = self.scorer(e_neg, pred.unsqueeze(2)).squeeze(-1)                                  # :493-500
+        logits = torch.cat([s_pos, s_neg], dim=2) / self.tau                                       # :511-514
+        logp = torch.log_softmax(logits, dim=-1)                                                   # :515, :660
+        m = mask.to(self.dtype)
+        denom = m.sum() if sum_mask_global is None else torch.tensor(float(sum_mask_global), dtype=self.dtype)
+        xe = -(logp[:, :, 0] * m).sum() / denom                                                    # :660-664
+        reg = torch.zeros((), dtype=self.dtype)
+        if self.reg > 0.0:
+            for name, w in self.params.items():
+                if self.regularised(name):
+                    reg = reg + self.reg * (w ** 2).sum() / 2.0                                    # l2_regularizer
+        total = xe + reg                                                                           # :667
+        return {'total_loss': total, 'xe_loss': xe, 'reg_loss': reg, 'logits': logits, 'mask': mask,
+                'x_in': x_in, 'x_pos': x_pos, 'x_neg': x_neg, 'e_in': e_in, 'e_pos': e_pos, 'e_neg': e_neg,
+                'rnn_out': r, 'pred': pred, 'probs': torch.softmax(logits, dim=-1)}
+
+    # ------------------------------------------------------------------ train
+    def compute_gradients(self, out) -> Dict[str, torch.Tensor]:
+        names = list(self.params.keys())
+        grads = torch.autograd.grad(out['total_loss'], [self.params[n] for n in names], allow_unused=True)
+        return {n: (g if g is not None else torch.zeros_like(self.params[n])) for n, g in zip(names, grads)}
+
+    def apply_gradients(self, grads: Dict[str, torch.Tensor]):
+        """tf.train.AdamOptimizer(lr, 0.9, 0.999, 1e-8) (nar_model.py:708-722): epsilon outside the
+        bias-corrected sqrt; sparse gradients are applied densely (moments of every row decay)."""
+        b1, b2, eps = 0.9, 0.999, 1e-8
+        self.step += 1
+        t = self.step
+        lr_t = self.lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
+        with torch.no_grad():
+            for n, p in self.params.items():
+                g = grads[n]
+                self.adam_m[n].mul_(b1).add_(g, alpha=1.0 - b1)
+                self.adam_v[n].mul_(b2).addcmul_(g, g, value=1.0 - b2)
+                p.sub_(lr_t * self.adam_m[n] / (self.adam_v[n].sqrt() + eps))
+
+    def train_step(self, features, labels, negatives, buffer, pop_norm, sum_mask_global=None):
+        out = self.forward(features, labels, negatives, buffer, pop_norm, sum_mask_global)
+        grads = self.compute_gradients(out)
+        self.apply_gradients(grads)
+        return out, grads

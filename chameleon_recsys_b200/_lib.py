@@ -52,6 +52,7 @@ _SIGNATURES = {
     'nar_ctx_destroy': (C.c_int, [vp]),
     'nar_gather_features': (C.c_int, [vp, C.POINTER(FeaturePlanC), vp, vp, i64, i64, i64, vp, vp, vp, vp]),
     'nar_gather_features_bwd': (C.c_int, [vp, C.POINTER(FeaturePlanC), vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, vp]),
+    'nar_build_rows': (C.c_int, [vp, i64, vp, vp, vp, i64, vp, vp, vp]),
     'nar_feature_stats': (C.c_int, [vp, vp, i64, i64, vp, vp, vp, f32, f32, vp, vp, i64, i64, i64, vp, vp, vp]),
     'nar_gather_rows_f32': (C.c_int, [vp, i64, i64, C.c_int, vp, i64, vp, i64, vp]),
     'nar_scatter_add_rows_f32': (C.c_int, [vp, i64, i64, C.c_int, vp, i64, vp, i64, vp]),

@@ -326,8 +326,37 @@ scatter_add_rows_kernel(float* __restrict__ table, int64_t n_table_rows, int64_t
   for (int j = lane; j < width; j += 32) atomicAdd(table + id * ld + j, src[r * ld_src + j]);
 }
 
+__global__ void __launch_bounds__(256)
+build_rows_kernel(const int32_t* __restrict__ pos_idx, int64_t L, const int64_t* __restrict__ item_clicked,
+                  const int64_t* __restrict__ label_next, const int64_t* __restrict__ negatives, int64_t K,
+                  int32_t* __restrict__ row_pos, int64_t* __restrict__ row_item) {
+  const int64_t n_cand = K + 1;
+  const int64_t total = L * (n_cand + 1);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t l = i / (n_cand + 1), j = i - l * (n_cand + 1);     // j = 0 input, 1 positive, 2.. negatives
+    const int32_t pos = pos_idx[l];
+    int64_t r, item;
+    if (j == 0) { r = l; item = item_clicked[pos]; }
+    else if (j == 1) { r = L + l * n_cand; item = label_next[pos]; }
+    else { r = L + l * n_cand + (j - 1); item = negatives[(int64_t)pos * K + (j - 2)]; }
+    row_pos[r] = pos;
+    row_item[r] = item;
+  }
+}
+
 }  // namespace feat
 }  // namespace nar
+
+extern "C" int nar_build_rows(const int32_t* pos_idx, int64_t L, const int64_t* item_clicked, const int64_t* label_next_item,
+                              const int64_t* negatives, int64_t K, int32_t* row_pos, int64_t* row_item, void* stream) {
+  if (!pos_idx || !item_clicked || !label_next_item || !negatives || !row_pos || !row_item || K < 0) return NAR_ERR_INVALID;
+  if (L <= 0) return NAR_OK;
+  const int64_t total = L * (K + 2);
+  int64_t g = (total + 255) / 256; if (g > 148 * 8) g = 148 * 8;
+  nar::feat::build_rows_kernel<<<(unsigned)g, 256, 0, as_stream(stream)>>>(pos_idx, L, item_clicked, label_next_item, negatives, K, row_pos, row_item);
+  NAR_LAUNCH_CHECK();
+  return NAR_OK;
+}
 
 extern "C" int nar_gather_features(nar_ctx* ctx, const nar_feature_plan* plan, const int32_t* row_pos,
                                    const int64_t* row_item, int64_t n_rows, int64_t n_input, int64_t n_cand,

@@ -121,13 +121,16 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
 
 // UMMA shared-memory descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
 //   [0,14) start>>4  [16,30) LBO>>4  [32,46) SBO>>4  [46,48) version=1  [61,64) layout (2 = SWIZZLE_128B)
-// K-major tile  (rows x 128 B, 8-row atoms 1024 B apart):            LBO unused (1), SBO = 1024
-// MN-major tile (k rows x 128 B of MN, 32-wide MN chunks 4096 B apart): LBO = 4096,    SBO = 1024
+// K-major tile  (rows x 128 B, 8-row atoms 1024 B apart): layout 2 (SWIZZLE_128B), LBO unused (1), SBO = 1024.
+// MN-major tile: 32-bit operands have ONE legal MN-major layout, SWIZZLE_128B_BASE32B (layout 1; CUTLASS
+// Layout_MN_SW128_32B_Atom = Swizzle<2,5,2>, 4 k-rows x 128 B of MN per atom; TMA SWIZZLE_128B_ATOM_32B):
+// k rows of 128 B, 4-row atoms 512 B apart (SBO), 32-wide MN chunks one TMA box = 4096 B apart (LBO).
 template <bool MN_MAJOR>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   const uint64_t lbo = MN_MAJOR ? (4096u >> 4) : 1u;
-  const uint64_t sbo = 1024u >> 4;
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (2ull << 61);
+  const uint64_t sbo = MN_MAJOR ? (512u >> 4) : (1024u >> 4);
+  const uint64_t layout = MN_MAJOR ? 1ull : 2ull;
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 
 // instruction descriptor (UMMA::InstrDescriptor): c_format F32 (1<<4), a/b format TF32 (2<<7, 2<<10),
@@ -333,7 +336,8 @@ static int make_operand_map(const nar_ctx* ctx, CUtensorMap* map, const float* p
   strides[0] = (cuuint64_t)ld * 4;
   CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
       map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, kmajor ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+      CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? NAR_OK : NAR_ERR_INVALID;
 }

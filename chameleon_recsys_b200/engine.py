@@ -1,0 +1,415 @@
+"""Device engine of the NAR hot path: owns the HBM-resident state (weights, Adam slots, ACR
+table, metadata) and runs one training / evaluation step as a sequence of libnar_b200 kernels
+on torch's current CUDA stream.  torch = allocator + streams + NCCL plumbing only.
+
+Step order follows the reference graph (nar_module/nar/nar_model.py):
+  sampler (:265-276) -> features (:314-370) -> CAR (:374-405) -> RNN (:408, :1308-1342) ->
+  FC1/FC2 (:410-438) -> scorer (:444-517) -> loss (:639-704) -> Adam (:706-722)
+with one structural difference: only the valid positions (mask == 1) are materialised.
+Padded positions never reach the loss (:660-664), so skipping them changes no output.
+
+HBM layout (per step; L = valid positions, n_cand = 1+K, R = L + L*n_cand rows):
+  X   [R, Fp]   feature rows: inputs [0,L), then per position: positive, K negatives
+  H1  [R, C]    leaky(X W1 + b1)         E [R, C]  tanh(H1 W2 + b2)  (CAR embeddings)
+  GX  [L, 2Hp]  x Wx + b per RNN layer   HO/GT/CD [L, Hp] state / gate / candidate
+  F1  [L, 512]  PR [L, C] predicted embedding
+  PD  [Rc, C]   cand * pred   Z1 [Rc,128] Z2 [Rc,64] Z3 [Rc,32]   logits [L, n_cand]
+Backward reuses the same buffers in place (dH1 over H1, dX over X, dprod over PD).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import ACT_LEAKY, ACT_NONE, ACT_TANH, FeaturePlanC, NarError
+from .plan import (SEG_ACR, SEG_CTX_EMBED, SEG_ITEM_EMB, SEG_META_EMBED, FeaturePlan, ParamLayout, round_up)
+
+
+class StepBatch:
+    """Host-side description of one step (numpy views) + device staging."""
+    pass
+
+
+class NarEngine:
+    def __init__(self, plan: FeaturePlan, layout: ParamLayout, content_article_embeddings_matrix: np.ndarray,
+                 articles_metadata: Dict[str, np.ndarray], *, negative_samples: int, negative_sample_from_buffer: int,
+                 softmax_temperature: float, reg_weight_decay: float, lr: float,
+                 recent_clicks_buffer_max_size: int, recent_clicks_for_normalization: int,
+                 elapsed_days_smooth_log_base: float = 1.3, popularity_smooth_log_base: float = 2.0,
+                 ranking: str = 'mlp', rnn_cell: str = 'ugrnn', sampler_seed: int = 42, device: Optional[int] = None,
+                 fwd_precision: int = 3, bwd_precision: int = 1, process_group=None, max_batch: int = 0):
+        if not torch.cuda.is_available():
+            raise NarError('NarEngine needs a CUDA (sm_100a) device; there is no CPU fallback')
+        if rnn_cell != 'ugrnn':
+            raise NotImplementedError("rnn_cell=%r: only the reference's UGRNNCell is implemented" % rnn_cell)
+        if ranking not in ('mlp', 'cosine'):
+            raise ValueError(ranking)
+        self.dev = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+        self.plan, self.layout = plan, layout
+        self.K = int(negative_samples)
+        self.n_from_buffer = int(negative_sample_from_buffer)
+        self.tau = float(softmax_temperature)
+        self.reg = float(reg_weight_decay)
+        self.lr = float(lr)
+        self.buf_len = int(recent_clicks_buffer_max_size)
+        self.n_norm = int(recent_clicks_for_normalization)
+        self.lb_rec, self.lb_nov = float(elapsed_days_smooth_log_base), float(popularity_smooth_log_base)
+        self.ranking = ranking
+        self.seed = int(sampler_seed)
+        self.fwd_prec, self.bwd_prec = int(fwd_precision), int(bwd_precision)
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        self.rank = torch.distributed.get_rank(process_group) if process_group is not None else 0
+        self.C, self.H, self.Hp, self.layers = layout.C, layout.H, layout.Hp, layout.layers
+        self.V = plan.num_items
+        d = self.dev
+        # ---- resident tables
+        acr = np.zeros((self.V, plan.acr_ld), dtype=np.float32)
+        acr[:, :plan.acr_dim] = np.asarray(content_article_embeddings_matrix, dtype=np.float32)
+        self.acr = torch.from_numpy(acr).to(d)
+        self.created_at = torch.from_numpy(np.asarray(articles_metadata['created_at_ts'], dtype=np.int64)).to(d)
+        self.meta = [torch.from_numpy(np.asarray(articles_metadata[n], dtype=np.int64)).to(d) for n in plan.meta_names]
+        # ---- parameters (flat fp32 buffers; same offsets for grads / Adam slots)
+        n = layout.total
+        self.params = torch.zeros(n, device=d)
+        self.grads = torch.zeros(n, device=d)
+        self.adam_m = torch.zeros(n, device=d)
+        self.adam_v = torch.zeros(n, device=d)
+        self.global_step = 0
+        self.WhT = [torch.zeros(2 * self.Hp, self.Hp, device=d) for _ in range(self.layers)]
+        self.stats = torch.zeros(24, device=d)
+        self.loss_dev = torch.zeros(4, device=d)          # [xe_sum, reg, -, -]
+        self.loss_host = torch.zeros(4).pin_memory()
+        self._bufs: Dict[str, torch.Tensor] = {}
+        self._pinned: Dict[str, torch.Tensor] = {}
+        self._sampler_ws = None
+        self.last: Dict[str, torch.Tensor] = {}
+        self.ops = ops
+        ops.context(self.dev.index)     # fail loudly here if the library / device is unusable
+
+    # ------------------------------------------------------------------ parameters
+    def view(self, key: str, buf: Optional[torch.Tensor] = None) -> torch.Tensor:
+        t = self.layout.by_key[key]
+        b = self.params if buf is None else buf
+        return b[t.offset:t.offset + t.size].view(t.rows, t.ld)
+
+    def set_params(self, logical: Dict[str, np.ndarray]):
+        flat = self.layout.to_internal(logical)
+        self.params.copy_(torch.from_numpy(flat))
+        self.adam_m.zero_(); self.adam_v.zero_(); self.grads.zero_()
+        self.global_step = 0
+
+    def get_params(self) -> Dict[str, np.ndarray]:
+        return self.layout.to_logical(self.params.detach().cpu().numpy())
+
+    def get_grads(self) -> Dict[str, np.ndarray]:
+        return self.layout.to_logical(self.grads.detach().cpu().numpy())
+
+    def state_dict(self) -> dict:
+        return {'params': self.layout.to_logical(self.params.cpu().numpy()),
+                'adam_m': self.layout.to_logical(self.adam_m.cpu().numpy()),
+                'adam_v': self.layout.to_logical(self.adam_v.cpu().numpy()),
+                'global_step': self.global_step}
+
+    def load_state_dict(self, sd: dict):
+        self.params.copy_(torch.from_numpy(self.layout.to_internal(sd['params'])))
+        self.adam_m.copy_(torch.from_numpy(self.layout.to_internal(sd['adam_m'])))
+        self.adam_v.copy_(torch.from_numpy(self.layout.to_internal(sd['adam_v'])))
+        self.global_step = int(sd['global_step'])
+
+    # ------------------------------------------------------------------ buffers
+    def _buf(self, name: str, rows: int, cols: int, dtype=torch.float32) -> torch.Tensor:
+        need = max(1, rows) * cols
+        t = self._bufs.get(name)
+        if t is None or t.numel() < need or t.dtype != dtype:
+            cap = int(need * 1.25) + 1024
+            t = torch.empty(cap, device=self.dev, dtype=dtype)
+            self._bufs[name] = t
+        return t[:max(1, rows) * cols].view(max(1, rows), cols)
+
+    def _pin(self, name: str, nbytes: int) -> torch.Tensor:
+        t = self._pinned.get(name)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8).pin_memory()
+            self._pinned[name] = t
+        return t
+
+    # ------------------------------------------------------------------ staging (host -> HBM, one copy)
+    def stage(self, features: Dict[str, np.ndarray], labels: Dict[str, np.ndarray], buffer: np.ndarray,
+              pop_norm: np.ndarray) -> dict:
+        """Pack the step inputs into one pinned buffer and issue one async H2D copy.
+        ``features``/``labels`` hold the GLOBAL batch (all data-parallel ranks see the same arrays)."""
+        item_clicked = np.ascontiguousarray(features['item_clicked'], dtype=np.int64)
+        Bg, T = item_clicked.shape
+        lens_g = np.clip(np.asarray(features['session_size'], dtype=np.int64) - 1, 0, T)
+        L_global = int(lens_g.sum())
+        per = Bg // self.world
+        if per * self.world != Bg:
+            raise ValueError('global batch %d not divisible by world size %d' % (Bg, self.world))
+        s0 = self.rank * per
+        lens = lens_g[s0:s0 + per]
+        L = int(lens.sum())
+        sess_off = np.zeros(per + 1, dtype=np.int32)
+        np.cumsum(lens, out=sess_off[1:])
+        # compact valid positions, session-major: flat index into the GLOBAL [Bg*T] arrays
+        tt = np.arange(T, dtype=np.int64)[None, :]
+        valid = tt < lens[:, None]
+        bb = (np.arange(per, dtype=np.int64) + s0)[:, None]
+        pos_idx = (bb * T + tt)[valid].astype(np.int32)
+        all_items = np.concatenate([item_clicked, np.asarray(labels['label_last_item'], dtype=np.int64).reshape(Bg, 1)], axis=1)
+        ev = np.ascontiguousarray(features['event_timestamp'], dtype=np.int64)
+        parts = [('all_items', all_items, np.int64), ('event_ts', ev, np.int64),
+                 ('item_clicked', item_clicked, np.int64),
+                 ('label_next', np.ascontiguousarray(labels['label_next_item'], dtype=np.int64), np.int64),
+                 ('buffer', np.ascontiguousarray(buffer, dtype=np.int64), np.int64),
+                 ('max_ts', np.asarray([ev.max() if ev.size else 0], dtype=np.int64), np.int64)]
+        for name in self.plan.ctx_int_names:
+            parts.append(('ci/' + name, np.ascontiguousarray(features[name], dtype=np.int64), np.int64))
+        parts.append(('pop_norm', np.ascontiguousarray(pop_norm, dtype=np.float32), np.float32))
+        for name in self.plan.ctx_float_names:
+            parts.append(('cf/' + name, np.ascontiguousarray(features[name], dtype=np.float32), np.float32))
+        parts.append(('pos_idx', pos_idx, np.int32))
+        parts.append(('sess_off', sess_off, np.int32))
+        offs, off = {}, 0
+        for name, arr, dt in parts:
+            off = round_up(off, 16)
+            offs[name] = (off, arr.size, dt, arr.shape)
+            off += arr.size * np.dtype(dt).itemsize
+        total = round_up(off, 16)
+        pin = self._pin('stage', total)
+        pin_np = pin.numpy()
+        for name, arr, dt in parts:
+            o, nel, _, _ = offs[name]
+            pin_np[o:o + nel * np.dtype(dt).itemsize].view(dt)[:] = arr.reshape(-1)
+        dev = self._buf('stage', total, 1, torch.uint8).view(-1)
+        dev[:total].copy_(pin[:total], non_blocking=True)
+        tmap = {np.int64: torch.int64, np.float32: torch.float32, np.int32: torch.int32}
+        tens = {}
+        for name, (o, nel, dt, shp) in offs.items():
+            tens[name] = dev[o:o + nel * np.dtype(dt).itemsize].view(tmap[dt]).view(*shp) if nel > 0 else \
+                torch.zeros(shp, dtype=tmap[dt], device=self.dev)
+        return {'t': tens, 'Bg': Bg, 'B': per, 'T': T, 'L': L, 'L_global': L_global, 's0': s0,
+                'h2d_bytes': total, 'lens': lens}
+
+    # ------------------------------------------------------------------ feature plan for this step
+    def _plan_c(self, st: dict) -> FeaturePlanC:
+        p = FeaturePlanC()
+        pl = self.plan
+        p.n_segments = len(pl.segments)
+        p.row_ld = pl.Fp
+        t = st['t']
+        for i, s in enumerate(pl.segments):
+            sg = p.seg[i]
+            sg.kind, sg.col, sg.width, sg.card, sg.src = s.kind, s.int_col, s.width, s.card, s.src
+            sg.ld, sg.table, sg.grad = 0, None, None
+            if s.kind == SEG_ACR:
+                sg.ld, sg.table = pl.acr_ld, self.acr.data_ptr()
+            elif s.kind in (SEG_ITEM_EMB, SEG_CTX_EMBED, SEG_META_EMBED):
+                pt = self.layout.by_key[s.param]
+                sg.ld = pt.ld
+                sg.table = self.params.data_ptr() + 4 * pt.offset
+                sg.grad = self.grads.data_ptr() + 4 * pt.offset
+        for i, n in enumerate(pl.ctx_int_names):
+            p.ctx_int[i] = t['ci/' + n].data_ptr()
+        for i, n in enumerate(pl.ctx_float_names):
+            p.ctx_float[i] = t['cf/' + n].data_ptr()
+        for i, m in enumerate(self.meta):
+            p.meta[i] = m.data_ptr()
+        p.created_at_ts = self.created_at.data_ptr()
+        p.pop_norm = t['pop_norm'].data_ptr()
+        p.gamma = self.view('gamma').data_ptr()
+        p.beta = self.view('beta').data_ptr()
+        p.stats = self.stats.data_ptr()
+        p.log_base_recency, p.log_base_novelty = self.lb_rec, self.lb_nov
+        return p
+
+    # ------------------------------------------------------------------ GEMM helpers
+    def _fwd(self, X, Wkey, bkey, Y, M, act, K=None, N=None):
+        W = self.view(Wkey)
+        K = W.shape[0] if K is None else K
+        N = W.shape[1] if N is None else N
+        ops.gemm(X, W, Y, M, N, K, a_kmajor=True, b_kmajor=False, bias=self.view(bkey).view(-1) if bkey else None,
+                 act=act, precision=self.fwd_prec)
+
+    def _dgrad(self, dY, Wkey, dX, M, dact=ACT_NONE, aux=None, N_out=None, K_in=None):
+        """dX[M, in] = dY[M, out] * W^T  (W stored [in, out]) optionally times act'(aux)."""
+        W = self.view(Wkey)
+        n_in = W.shape[0] if N_out is None else N_out
+        n_out = W.shape[1] if K_in is None else K_in
+        ops.gemm(dY, W, dX, M, n_in, n_out, a_kmajor=True, b_kmajor=True, dact=dact, aux=aux, precision=self.bwd_prec)
+
+    def _split(self, M, N, Kred) -> int:
+        tiles = ((M + 127) // 128) * ((N + 127) // 128)
+        kt = (Kred + 31) // 32
+        s = max(1, min((2 * 148 + tiles - 1) // tiles, kt // 4 if kt >= 4 else 1))
+        return s
+
+    def _wgrad(self, X, dY, Wkey, rows, n_in=None, n_out=None):
+        """dW[in, out] += X[rows, in]^T * dY[rows, out]  (split-K, atomics into the grad buffer)."""
+        dW = self.view(Wkey, self.grads)
+        n_in = dW.shape[0] if n_in is None else n_in
+        n_out = dW.shape[1] if n_out is None else n_out
+        ops.gemm(X, dY, dW, n_in, n_out, rows, a_kmajor=False, b_kmajor=False, accumulate=True,
+                 split_k=self._split(n_in, n_out, rows), precision=self.bwd_prec)
+
+    def _bgrad(self, dY, bkey, rows, cols):
+        ops.colsum_add(dY, rows, cols, dY.stride(0), self.view(bkey, self.grads).view(-1))
+
+    # ------------------------------------------------------------------ the step
+    def step(self, st: dict, train: bool = True, keep: bool = False) -> dict:
+        """Run one step on staged inputs.  Returns device tensors (loss parts, logits, negatives)."""
+        t = st['t']
+        B, Bg, T, L, s0 = st['B'], st['Bg'], st['T'], st['L'], st['s0']
+        K, C_, Hp, Fp = self.K, self.C, self.Hp, self.plan.Fp
+        n_cand = K + 1
+        Rc = L * n_cand
+        R = L + Rc
+        inv_count = 1.0 / max(1, st['L_global'])
+        step_id = self.global_step + 1
+        self.loss_dev.zero_()
+        # ---- negatives (nar_model.py:265-276)
+        need = ops.sample_negatives_workspace(Bg, T + 1, self.buf_len, K)
+        if self._sampler_ws is None or self._sampler_ws.numel() < need:
+            self._sampler_ws = torch.zeros(need, dtype=torch.uint8, device=self.dev)
+        neg = self._buf('neg', Bg * T, K, torch.int64)
+        if B < Bg:
+            neg.zero_()
+        neg_local = neg.view(-1)[s0 * T * K:(s0 + B) * T * K].view(B, T, K)
+        ops.sample_negatives(t['all_items'], s0, B, t['buffer'], K, self.n_from_buffer, self.seed, step_id, neg_local,
+                             self._sampler_ws)
+        out = {'negatives': neg_local, 'L': L}
+        if L == 0:
+            out.update(loss=self.loss_dev, logits=None)
+            return out
+        # ---- row lists + features (nar_model.py:314-370)
+        row_pos = self._buf('row_pos', R, 1, torch.int32).view(-1)
+        row_item = self._buf('row_item', R, 1, torch.int64).view(-1)
+        ops.build_rows(t['pos_idx'], L, t['item_clicked'], t['label_next'], neg, K, row_pos, row_item)
+        ops.feature_stats(t['buffer'], self.n_norm, self.created_at, t['pop_norm'], t['max_ts'], self.lb_rec, self.lb_nov,
+                          row_pos, row_item, R, L, n_cand, t['event_ts'], self.stats)
+        planc = self._plan_c(st)
+        X = self._buf('X', R, Fp)
+        ops.gather_features(planc, row_pos, row_item, R, L, n_cand, t['event_ts'], t['max_ts'], X)
+        # ---- CAR (nar_model.py:374-405)
+        H1 = self._buf('H1', R, C_)
+        E = self._buf('E', R, C_)
+        self._fwd(X, 'W1', 'b1', H1, R, ACT_LEAKY)
+        self._fwd(H1, 'W2', 'b2', E, R, ACT_TANH)
+        # ---- RNN (nar_model.py:408, :1308-1342)
+        rnn_in = E
+        HO, GT, CD, GX = [], [], [], []
+        for i in range(self.layers):
+            gx = self._buf('GX%d' % i, L, 2 * Hp)
+            ho = self._buf('HO%d' % i, L, Hp); gt = self._buf('GT%d' % i, L, Hp); cd = self._buf('CD%d' % i, L, Hp)
+            self._fwd(rnn_in, 'rnn%d/Wx' % i, 'rnn%d/b' % i, gx, L, ACT_NONE)
+            ops.ugrnn_fwd(gx, self.view('rnn%d/Wh' % i), t['sess_off'], B, Hp, ho, gt, cd)
+            HO.append(ho); GT.append(gt); CD.append(cd); GX.append(gx)
+            rnn_in = ho
+        # ---- session representation (nar_model.py:410-438)
+        F1 = self._buf('F1', L, 512)
+        PR = self._buf('PR', L, C_)
+        self._fwd(HO[-1], 'W3', 'b3', F1, L, ACT_LEAKY)
+        self._fwd(F1, 'W4', 'b4', PR, L, ACT_TANH)
+        # ---- scorer + loss (nar_model.py:444-517, :639-667)
+        Ec = E[L:]
+        logits = self._buf('logits', L, n_cand)
+        dE = self._buf('dE', R, C_) if train else None
+        dPR = self._buf('dPR', L, C_) if train else None
+        if self.ranking == 'mlp':
+            PD = self._buf('PD', Rc, C_)
+            Z1 = self._buf('Z1', Rc, 128); Z2 = self._buf('Z2', Rc, 64); Z3 = self._buf('Z3', Rc, 32)
+            ops.mul_pred(Ec, PR, L, n_cand, C_, PD)
+            self._fwd(PD, 'M1', 'c1', Z1, Rc, ACT_LEAKY)
+            self._fwd(Z1, 'M2', 'c2', Z2, Rc, ACT_LEAKY)
+            self._fwd(Z2, 'M3', 'c3', Z3, Rc, ACT_LEAKY)
+            dZ3 = self._buf('dZ3', Rc, 32) if train else None
+            m4 = self.view('M4'); c4 = self.view('c4')
+            ops.score_softmax_ce(Z3, 32, 32, m4, m4.stride(0), c4, L, n_cand, 1.0 / self.tau, inv_count, logits,
+                                 self.loss_dev[0:1], dZ3, self.view('M4', self.grads) if train else None,
+                                 self.view('c4', self.grads) if train else None)
+        else:
+            ops.cosine_softmax_ce(Ec, PR, L, n_cand, C_, 1.0 / self.tau, inv_count, logits, self.loss_dev[0:1],
+                                  dE[L:] if train else None, dPR)
+        if self.reg > 0.0:
+            # every rank holds the same weights: add the regulariser once (rank 0) so that the sum-allreduce is exact
+            if self.rank == 0:
+                ops.l2_loss_add(self.params, self.layout.reg_end, self.reg, self.loss_dev[1:2])
+        out.update(loss=self.loss_dev, logits=logits)
+        if keep:
+            self.last = dict(X=X, H1=H1, E=E, HO=HO, F1=F1, PR=PR, logits=logits, row_pos=row_pos, row_item=row_item,
+                             stats=self.stats, neg=neg_local)
+        if not train:
+            return out
+        # =================================================================== backward
+        if self.ranking == 'mlp':
+            dZ2 = self._buf('dZ2', Rc, 64); dZ1 = self._buf('dZ1', Rc, 128)
+            self._wgrad(Z2, dZ3, 'M3', Rc); self._bgrad(dZ3, 'c3', Rc, 32)
+            self._dgrad(dZ3, 'M3', dZ2, Rc, dact=ACT_LEAKY, aux=Z2)
+            self._wgrad(Z1, dZ2, 'M2', Rc); self._bgrad(dZ2, 'c2', Rc, 64)
+            self._dgrad(dZ2, 'M2', dZ1, Rc, dact=ACT_LEAKY, aux=Z1)
+            self._wgrad(PD, dZ1, 'M1', Rc); self._bgrad(dZ1, 'c1', Rc, 128)
+            self._dgrad(dZ1, 'M1', PD, Rc)                       # d(prod) over PD in place (wgrad was issued first)
+            ops.mul_pred_bwd(PD, Ec, PR, L, n_cand, C_, dE[L:], dPR)
+        # candidate rows: through the CAR tanh
+        ops.act_bwd(dE[L:], Ec, Rc * C_, ACT_TANH, dE[L:])
+        # FC2 / FC1 (nar_model.py:410-426)
+        ops.act_bwd(dPR, PR, L * C_, ACT_TANH, dPR)
+        self._wgrad(F1, dPR, 'W4', L); self._bgrad(dPR, 'b4', L, C_)
+        dF1 = self._buf('dF1', L, 512)
+        self._dgrad(dPR, 'W4', dF1, L, dact=ACT_LEAKY, aux=F1)
+        self._wgrad(HO[-1], dF1, 'W3', L); self._bgrad(dF1, 'b3', L, 512)
+        dHO = self._buf('dHO', L, Hp)
+        self._dgrad(dF1, 'W3', dHO, L)
+        # RNN BPTT
+        for i in reversed(range(self.layers)):
+            Wh = self.view('rnn%d/Wh' % i)
+            ops.transpose(Wh, Hp, 2 * Hp, 2 * Hp, self.WhT[i], Hp)
+            dGX = self._buf('dGX', L, 2 * Hp); HPV = self._buf('HPV', L, Hp)
+            ops.ugrnn_bwd(dHO, HO[i], GT[i], CD[i], self.WhT[i], t['sess_off'], B, Hp, dGX, HPV)
+            x_in = E if i == 0 else HO[i - 1]
+            self._wgrad(x_in, dGX, 'rnn%d/Wx' % i, L)
+            self._wgrad(HPV, dGX, 'rnn%d/Wh' % i, L)
+            self._bgrad(dGX, 'rnn%d/b' % i, L, 2 * Hp)
+            if i == 0:
+                self._dgrad(dGX, 'rnn0/Wx', dE, L, dact=ACT_TANH, aux=E)      # input rows of dE (pre-tanh)
+            else:
+                dprev = self._buf('dHO_b', L, Hp)
+                self._dgrad(dGX, 'rnn%d/Wx' % i, dprev, L)
+                dHO = dprev
+        # CAR (shared weights: inputs + positives + negatives in one GEMM)
+        self._wgrad(H1, dE, 'W2', R); self._bgrad(dE, 'b2', R, C_)
+        self._dgrad(dE, 'W2', H1, R, dact=ACT_LEAKY, aux=H1)       # dH1(pre) over H1 in place
+        self._wgrad(X, H1, 'W1', R); self._bgrad(H1, 'b1', R, C_)
+        self._dgrad(H1, 'W1', X, R)                                 # dX over X in place
+        ops.gather_features_bwd(planc, row_pos, row_item, R, L, n_cand, t['event_ts'], t['max_ts'], X,
+                                self.view('gamma', self.grads).view(-1), self.view('beta', self.grads).view(-1))
+        return out
+
+    def apply_gradients(self):
+        """NCCL sum-allreduce of the flat gradient buffer (data parallel), then TF-Adam."""
+        if self.world > 1:
+            torch.distributed.all_reduce(self.grads, group=self.pg)
+        self.global_step += 1
+        ops.adam_tf(self.params, self.grads, self.adam_m, self.adam_v, self.layout.total, self.layout.reg_end,
+                    self.reg, self.lr, self.global_step)
+
+    def train_step(self, features, labels, buffer, pop_norm, keep: bool = False, sync: bool = True) -> dict:
+        st = self.stage(features, labels, buffer, pop_norm)
+        self.grads.zero_()
+        out = self.step(st, train=True, keep=keep)
+        if st['L'] > 0 or self.world > 1:
+            self.apply_gradients()
+        if self.world > 1:
+            torch.distributed.all_reduce(self.loss_dev, group=self.pg)
+        self.loss_host.copy_(self.loss_dev, non_blocking=True)
+        out['stage'] = st
+        if sync:
+            torch.cuda.current_stream().synchronize()
+            out['xe_loss'] = float(self.loss_host[0]); out['reg_loss'] = float(self.loss_host[1])
+            out['total_loss'] = out['xe_loss'] + out['reg_loss']
+        return out

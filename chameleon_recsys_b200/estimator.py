@@ -1,0 +1,157 @@
+"""Estimator-shaped boundary of the NAR hot path (the reference's drop-in surface).
+
+* ``nar_module_model_fn(features, labels, mode, params)`` - nar_trainer_gcom.py:234-332: picks the
+  train / eval negative-sampling hparams by mode (:237-242), forces keep_prob 1 in eval (:245),
+  builds ``NARModuleModel`` (:252-275) and returns an ``EstimatorSpec`` with ``loss``, ``train_op``
+  and the ``ItemsStateUpdaterHook`` as training chief hook (:305-322).
+* ``build_estimator`` / ``Estimator.train`` - nar_trainer_gcom.py:335-386, :511-517: the minimal
+  MonitoredTrainingSession loop: hook.before_run -> train_op -> hook.after_run per batch.
+
+Differences that are inherent to not being a TF graph: ``features``/``labels`` are numpy dicts
+(one padded batch, same keys / dtypes / padding as datasets.py), ``train_op`` is a callable, and
+the model object is cached across ``train()`` calls instead of being rebuilt from a checkpoint.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional
+
+import numpy as np
+
+from .clicked_items_state import ClickedItemsState
+from .datasets import OutOfRangeError
+from .hparams import ModeKeys, get_internal_enabled_features_config
+from .nar_model import ItemsStateUpdaterHook, NARModuleModel
+
+# Global vars updated by the Estimator hook (nar_trainer_gcom.py:410-415)
+clicked_items_state: Optional[ClickedItemsState] = None
+eval_sessions_metrics_log: list = []
+
+
+@dataclass
+class EstimatorSpec:
+    mode: str
+    loss: Optional[float] = None
+    train_op: Optional[Callable] = None
+    training_chief_hooks: List = field(default_factory=list)
+    eval_metric_ops: Optional[dict] = None
+    evaluation_hooks: List = field(default_factory=list)
+    model: Optional[NARModuleModel] = None
+
+
+def nar_module_model_fn(features, labels, mode, params) -> EstimatorSpec:
+    if mode == ModeKeys.TRAIN:
+        negative_samples = params['train_total_negative_samples']
+        negative_sample_from_buffer = params['train_negative_samples_from_buffer']
+    elif mode == ModeKeys.EVAL:
+        negative_samples = params['eval_total_negative_samples']
+        negative_sample_from_buffer = params['eval_negative_samples_from_buffer']
+    else:
+        raise ValueError('mode %r' % (mode,))
+    dropout_keep_prob = params['dropout_keep_prob'] if mode == ModeKeys.TRAIN else 1.0
+    internal_features_config = params.get('internal_features_config') or get_internal_enabled_features_config()
+    eval_metrics_top_n = params['eval_metrics_top_n']
+
+    model = NARModuleModel(mode, features, labels,
+                           session_features_config=params['session_features_config'],
+                           articles_features_config=params['articles_features_config'],
+                           batch_size=params['batch_size'],
+                           lr=params['lr'],
+                           keep_prob=dropout_keep_prob,
+                           negative_samples=negative_samples,
+                           negative_sample_from_buffer=negative_sample_from_buffer,
+                           reg_weight_decay=params['reg_weight_decay'],
+                           softmax_temperature=params['softmax_temperature'],
+                           articles_metadata=params['articles_metadata'],
+                           content_article_embeddings_matrix=params['content_article_embeddings_matrix'],
+                           recent_clicks_buffer_hours=params['recent_clicks_buffer_hours'],
+                           recent_clicks_buffer_max_size=params['recent_clicks_buffer_max_size'],
+                           recent_clicks_for_normalization=params['recent_clicks_for_normalization'],
+                           CAR_embedding_size=params['CAR_embedding_size'],
+                           rnn_units=params['rnn_units'],
+                           rnn_num_layers=params.get('rnn_num_layers', 1),
+                           metrics_top_n=eval_metrics_top_n,
+                           plot_histograms=params['save_histograms'],
+                           novelty_reg_factor=params['novelty_reg_factor'],
+                           diversity_reg_factor=params['diversity_reg_factor'],
+                           internal_features_config=internal_features_config,
+                           eval_cold_start=params['eval_cold_start'],
+                           elapsed_days_smooth_log_base=params.get('elapsed_days_smooth_log_base', 1.3),
+                           popularity_smooth_log_base=params.get('popularity_smooth_log_base', 2.0),
+                           max_cardinality_for_ohe=params.get('max_cardinality_for_ohe', 10),
+                           rnn_cell=params.get('rnn_cell', 'ugrnn'), ranking=params.get('ranking', 'mlp'),
+                           sampler_seed=params.get('sampler_seed', 42), init_seed=params.get('init_seed', 42),
+                           process_group=params.get('process_group'), device=params.get('device'))
+
+    state = params.get('clicked_items_state') or clicked_items_state
+    if state is None:
+        raise RuntimeError('clicked_items_state is not set (nar_trainer_gcom.py:486-489 creates it before the Estimator)')
+    hooks = [ItemsStateUpdaterHook(mode, model, eval_metrics_top_n=eval_metrics_top_n, clicked_items_state=state,
+                                   eval_sessions_metrics_log=eval_sessions_metrics_log,
+                                   content_article_embeddings_matrix=params['content_article_embeddings_matrix'],
+                                   articles_metadata=params['articles_metadata'])]
+    if mode == ModeKeys.TRAIN:
+        def train_op(feats, labs, feed, sync=True):
+            return model.train(feats, labs, feed['pop_recent_items_buffer'], feed['articles_recent_pop_norm'], sync=sync)
+        return EstimatorSpec(mode, loss=None, train_op=train_op, training_chief_hooks=hooks, model=model)
+    raise NotImplementedError('ModeKeys.EVAL is a "next" row (SURVEY.md section 8f #2)')
+
+
+class Estimator:
+    """tf.estimator.Estimator stand-in: ``train(input_fn, steps=None)`` runs the hook/train_op loop."""
+
+    def __init__(self, model_fn, params, model_dir=None, config=None):
+        self.model_fn = model_fn
+        self.params = params
+        self.model_dir = model_dir
+        self._spec: Optional[EstimatorSpec] = None
+        self.last_loss = None
+        self.interactions = 0
+
+    def _ensure_spec(self, features, labels) -> EstimatorSpec:
+        if self._spec is None:
+            self._spec = self.model_fn(features, labels, ModeKeys.TRAIN, self.params)
+        return self._spec
+
+    def train(self, input_fn, steps: Optional[int] = None, hooks=None):
+        it = input_fn()
+        n = 0
+        spec = None
+        while steps is None or n < steps:
+            try:
+                features, labels = it.get_next() if hasattr(it, 'get_next') else next(it)
+            except (OutOfRangeError, StopIteration):
+                break
+            spec = self._ensure_spec(features, labels)
+            if n == 0:
+                for h in spec.training_chief_hooks:
+                    h.begin()
+            feed = {}
+            for h in spec.training_chief_hooks:
+                feed.update(h.before_run(None))
+            out = spec.train_op(features, labels, feed)
+            run_values = {'clicked_items': features['item_clicked'], 'clicked_timestamps': features['event_timestamp'],
+                          'last_item_label': labels['label_last_item']}
+            for h in spec.training_chief_hooks:
+                h.after_run(None, run_values)
+            self.last_loss = out.get('total_loss')
+            self.interactions += int(out['stage']['L_global'])
+            n += 1
+        if spec is not None:
+            for h in spec.training_chief_hooks:
+                h.end()
+        return self
+
+    @property
+    def model(self) -> Optional[NARModuleModel]:
+        return None if self._spec is None else self._spec.model
+
+
+def build_estimator(model_dir, content_article_embeddings_matrix, articles_metadata, articles_features_config,
+                    session_features_config, hparams, state: ClickedItemsState, **extra) -> Estimator:
+    """nar_trainer_gcom.py:335-386 with the flags carried by ``hparams`` (NARHParams)."""
+    params = hparams.to_params(session_features_config, articles_features_config, articles_metadata,
+                               content_article_embeddings_matrix)
+    params['clicked_items_state'] = state
+    params.update(extra)
+    return Estimator(model_fn=nar_module_model_fn, params=params, model_dir=model_dir)

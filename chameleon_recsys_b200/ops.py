@@ -78,6 +78,11 @@ def gather_features_bwd(plan: FeaturePlanC, row_pos, row_item, n_rows, n_input, 
           'nar_gather_features_bwd')
 
 
+def build_rows(pos_idx, L, item_clicked, label_next, negatives, K, row_pos, row_item):
+    check(_lib.load().nar_build_rows(_p(pos_idx), L, _p(item_clicked), _p(label_next), _p(negatives), K, _p(row_pos),
+                                     _p(row_item), _stream()), 'nar_build_rows')
+
+
 def feature_stats(buffer, n_norm, created_at_ts, pop_norm, max_ts, log_base_rec, log_base_nov, row_pos, row_item,
                   n_rows, n_input, n_cand, event_ts, stats):
     ctx = context()

@@ -98,6 +98,13 @@ int nar_gather_features_bwd(nar_ctx* ctx, const nar_feature_plan* plan /*host*/,
                             int64_t n_cand, const int64_t* event_timestamp, const int64_t* max_ts,
                             const float* d_out /*[n_rows,row_ld]*/, float* d_gamma, float* d_beta, void* stream);
 
+/* row lists of one step.  The L valid positions (pos_idx[l] = b*T+t, session-major) produce
+ * n_rows = L + L*(1+K) rows: input rows [0,L) = clicked items (nar_model.py:328), then for each
+ * position its candidates contiguously: positive label_next_item (:343) followed by its K
+ * negatives (:356).                                                                        */
+int nar_build_rows(const int32_t* pos_idx, int64_t L, const int64_t* item_clicked, const int64_t* label_next_item,
+                   const int64_t* negatives /*[B*T,K]*/, int64_t K, int32_t* row_pos, int64_t* row_item, void* stream);
+
 /* normalisation statistics of recency / novelty over the first n_norm nonzero buffer entries
  * (nar_model.py:1062-1089, :1150-1193, :1011-1039).  stats[g][8], g = 0 input / 1 positive /
  * 2 negative rows: {rec_mean, rec_std, rec_zmin, rec_zmax, nov_mean, nov_std, nov_zmin, nov_zmax};

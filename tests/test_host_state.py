@@ -1,0 +1,96 @@
+"""ClickedItemsState / datasets / plan (host logic) against fixtures generated from the reference's own
+classes (tests/golden/make_state_golden.py) and against the reference's documented semantics."""
+import os
+
+import numpy as np
+import pytest
+
+from chameleon_recsys_b200.clicked_items_state import ClickedItemsState, batch_clicks_for_state_update
+from chameleon_recsys_b200.datasets import OutOfRangeError, parse_sequence_example, prepare_dataset_iterator
+from chameleon_recsys_b200.harness import make_problem
+from chameleon_recsys_b200.hparams import get_embedding_size, workload
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def test_state_matches_reference_golden():
+    g = np.load(os.path.join(HERE, 'golden', 'state_golden.npz'))
+    for ci in range(3):
+        hours, max_size, n_norm, V = g['c%d_cfg' % ci]
+        st = ClickedItemsState(float(hours), int(max_size), int(n_norm), int(V))
+        for step in range(6):
+            st.update_items_state(g['c%d_items_%d' % (ci, step)], g['c%d_ts_%d' % (ci, step)])
+            assert np.array_equal(st.pop_recent_clicks_buffer, g['c%d_buffer_%d' % (ci, step)])
+            assert np.array_equal(st.get_articles_recent_pop(), g['c%d_recent_pop_%d' % (ci, step)])
+            assert np.array_equal(st.get_articles_recent_pop_norm(), g['c%d_pop_norm_%d' % (ci, step)])
+            assert np.array_equal(st.get_articles_pop(), g['c%d_pop_%d' % (ci, step)])
+
+
+def test_state_invariants():
+    st = ClickedItemsState(1.0, 50, 10, 100)
+    assert st.get_recent_clicks_buffer().shape == (50,) and not st.get_recent_clicks_buffer().any()
+    assert np.all(st.get_articles_recent_pop_norm() == 0.1)
+    t0 = 1_000_000_000
+    st.update_items_state(np.array([5, 6, 7]), np.array([t0, t0 + 1, t0 + 2]))
+    assert list(st.get_recent_clicks_buffer()[:4]) == [7, 6, 5, 0]            # newest first
+    st.update_items_state(np.array([8]), np.array([t0 + 2 * 3600 * 1000]))     # two hours later: old clicks dropped
+    assert list(st.get_recent_clicks_buffer()[:2]) == [8, 0]
+    assert st.get_articles_recent_pop_norm().min() >= 1.0 / 10
+    st.save_state_checkpoint()
+    st.update_items_state(np.array([9]), np.array([t0 + 2 * 3600 * 1000 + 5]))
+    st.restore_state_checkpoint()
+    assert list(st.get_recent_clicks_buffer()[:2]) == [8, 0]
+
+
+def test_batch_clicks_for_state_update():
+    items = np.array([[3, 4, 0], [5, 0, 0]]); ts = np.array([[10, 20, 0], [30, 0, 0]]); last = np.array([[9], [8]])
+    i, t = batch_clicks_for_state_update(items, ts, last)
+    assert list(i) == [3, 4, 9, 5, 8]
+    assert list(t) == [10, 20, 20, 30, 30]          # last label inherits the session's max timestamp (:1641-1643)
+
+
+def test_parse_sequence_example_labels_and_truncation():
+    cfg = {'single_features': {'session_size': {'dtype': 'int'}, 'user_id': {'dtype': 'int'}},
+           'sequence_features': {'item_clicked': {'dtype': 'int'}, 'event_timestamp': {'dtype': 'int'},
+                                 'x': {'dtype': 'float'}}}
+    ex = {'session_size': 6, 'user_id': 3, 'item_clicked': [1, 2, 3, 4, 5, 6], 'event_timestamp': [10, 20, 30, 40, 50, 60],
+          'x': [.1, .2, .3, .4, .5, .6]}
+    p = parse_sequence_example(ex, cfg, truncate_sequence_length=4)
+    assert p['session_size'] == 4
+    assert list(p['item_clicked']) == [1, 2, 3] and list(p['label_next_item']) == [2, 3, 4] and list(p['label_last_item']) == [4]
+    assert p['x'].dtype == np.float32 and p['item_clicked'].dtype == np.int64
+    it = prepare_dataset_iterator([ex, dict(ex, session_size=2, item_clicked=[7, 8], event_timestamp=[1, 2], x=[1., 2.])],
+                                  cfg, batch_size=2, truncate_session_length=4)
+    f, l = it.get_next()
+    assert f['item_clicked'].tolist() == [[1, 2, 3], [7, 0, 0]] and l['label_next_item'].tolist() == [[2, 3, 4], [8, 0, 0]]
+    assert l['label_last_item'].tolist() == [[4], [8]] and f['session_size'].tolist() == [4, 2]
+    with pytest.raises(OutOfRangeError):
+        it.get_next()
+
+
+def test_plan_and_layout_roundtrip():
+    assert get_embedding_size(46034) == 117 and get_embedding_size(461) == 37 and get_embedding_size(1000) == 44
+    for prof, F in (('A', 1 + 250 + 117), ('B', 71 + 37 + 250 + 117 + 2)):
+        pb = make_problem(workload('g1', prof), batch_size=4)
+        assert pb.plan.F == F and pb.plan.Fp % 4 == 0
+        for s in pb.plan.segments:
+            if s.name in ('acr', 'item_emb'):
+                assert s.int_col % 4 == 0
+        assert sorted(pb.plan.int2log[pb.plan.int2log >= 0].tolist()) == list(range(F))
+        if prof == 'B':       # the item table is large; check the round trip on the small profile only once
+            continue
+        logical = pb.layout.init_logical(1)
+        flat = pb.layout.to_internal(logical)
+        back = pb.layout.to_logical(flat)
+        for k in logical:
+            assert np.array_equal(logical[k], back[k]), k
+        # padding stays zero
+        total_logical = sum(v.size for v in logical.values())
+        assert np.count_nonzero(flat) <= total_logical
+    pbt = make_problem('tiny', profile='B')
+    names = pbt.layout.logical_names()
+    assert 'main/RNN/rnn/multi_rnn_cell/cell_0/ugrnn_cell/kernel' in names
+    lg = pbt.layout.init_logical(3)
+    assert lg['main/RNN/rnn/multi_rnn_cell/cell_0/ugrnn_cell/kernel'].shape == (64 + 64, 128)
+    assert np.array_equal(pbt.layout.to_logical(pbt.layout.to_internal(lg))['main/RNN/rnn/multi_rnn_cell/cell_0/ugrnn_cell/kernel'],
+                          lg['main/RNN/rnn/multi_rnn_cell/cell_0/ugrnn_cell/kernel'])

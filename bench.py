@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py - NAR train interactions/s on B200 (BASELINE.json metric), one JSON line on rank 0.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo (CUDA)
+  python bench.py --impl reference --gpus N --steps K --warmup W   # reference CPU path (oracle port)
+
+A "step" = one pass of the NAR training hot path over one batch of synthetic G1-shaped sessions
+(sampler -> feature gather -> CAR -> UGRNN -> FC -> scorer -> softmax-CE -> backward -> TF-Adam).
+  value : interactions/s with the step inputs already resident in HBM (CUDA events over K steps)
+  e2e   : the same metric through the reference-facing API (Estimator.train: model_fn / input_fn /
+          ItemsStateUpdaterHook) with HOST numpy batches: per step one pinned H2D copy of the inputs,
+          the host ClickedItemsState update and a D2H read of the loss, all inside the timed region
+  roofline        : the dominant kernel (CAR GEMM, tensor bound) timed alone, vs MEASURED_PEAKS.json
+  roofline_gather : the embedding-gather kernel (HBM bound; the kernel north_star names)
+  cpu_baseline    : the oracle (torch-CPU restatement of the TF1.12 graph) on the same workload
+Data parallel (N > 1, torchrun): weak scaling, per-GPU batch fixed, global batch = N x batch;
+sessions are sharded, the sampler sees the global batch, dense + embedding grads are sum-allreduced (NCCL).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def _peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get('hbm_gbs', 6650.0), d.get('bf16_tflops', 1590.0), d.get('bf16_tflops_sustained', 1400.0), 'measured'
+    return 6650.0, 1590.0, 1400.0, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            f = [x.strip() for x in r.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def make_batches(pb, n, global_batch, snapshot_at=None):
+    """n host batches + the host state (buffer, pop_norm) each step sees; state advances like the hook does.
+    With snapshot_at=i also returns a deep copy of the ClickedItemsState as it was before batch i."""
+    import copy
+    from chameleon_recsys_b200.clicked_items_state import batch_clicks_for_state_update
+    it = pb.input_fn(batch_size=global_batch)
+    out = []
+    snap = None
+    for i in range(n):
+        if snapshot_at is not None and i == snapshot_at:
+            snap = copy.deepcopy(pb.clicked_items_state)
+        f, l = it.get_next()
+        buf = pb.clicked_items_state.get_recent_clicks_buffer().copy()
+        pop = pb.clicked_items_state.get_articles_recent_pop_norm().astype(np.float32)
+        out.append((f, l, buf, pop))
+        items, ts = batch_clicks_for_state_update(f['item_clicked'], f['event_timestamp'], l['label_last_item'])
+        pb.clicked_items_state.update_items_state(items, ts)
+    return out if snapshot_at is None else (out, snap)
+
+
+def interactions(batch):
+    f = batch[0]
+    T = f['item_clicked'].shape[1]
+    return int(np.clip(f['session_size'] - 1, 0, T).sum())
+
+
+def oracle_for(pb):
+    import torch
+    from oracle.nar_oracle import NarOracle
+    hp = pb.hp
+    o = NarOracle(pb.session_features_config, pb.articles_features_config, pb.internal_features_config,
+                  pb.content_article_embeddings_matrix, pb.articles_metadata,
+                  negative_samples=hp.train_total_negative_samples, softmax_temperature=hp.softmax_temperature,
+                  reg_weight_decay=hp.reg_l2, recent_clicks_for_normalization=hp.recent_clicks_for_normalization,
+                  elapsed_days_smooth_log_base=hp.elapsed_days_smooth_log_base,
+                  popularity_smooth_log_base=hp.popularity_smooth_log_base, CAR_embedding_size=hp.CAR_embedding_size,
+                  rnn_units=hp.rnn_units, rnn_num_layers=hp.rnn_num_layers, lr=hp.learning_rate, ranking=hp.ranking,
+                  dtype=torch.float32)
+    o.set_params(pb.layout.init_logical(hp.init_seed))
+    return o
+
+
+def time_oracle(pb, batches, warmup, steps):
+    """Reference CPU path: full train step (sampler + fwd + bwd + TF-Adam + host state is pre-applied) per batch."""
+    import torch
+    from oracle import sampler_ref
+    torch.set_num_threads(os.cpu_count() or 1)
+    hp = pb.hp
+    o = oracle_for(pb)
+    n_int, t_total = 0, 0.0
+    for i, (f, l, buf, pop) in enumerate(batches[:warmup + steps]):
+        t0 = time.perf_counter()
+        allc = np.concatenate([f['item_clicked'], l['label_last_item']], axis=1)
+        neg = sampler_ref.sample_negatives(allc, buf, hp.train_total_negative_samples,
+                                           hp.train_negative_samples_from_buffer, hp.sampler_seed, i + 1)
+        o.train_step(f, l, neg, buf, pop)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            t_total += dt
+            n_int += interactions((f, l))
+    return n_int / t_total, t_total / max(1, steps), torch.get_num_threads()
+
+
+def run_reference(args):
+    from chameleon_recsys_b200.harness import make_problem, warm_state
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    pb = make_problem(args.workload, profile=args.profile, session_len=args.session_len)
+    gb = pb.hp.batch_size * args.gpus
+    warm_state(pb, args.state_warmup)
+    batches = make_batches(pb, args.warmup + args.steps, gb)
+    v, sec_per_step, cores = time_oracle(pb, batches, args.warmup, args.steps)
+    line = {'impl': 'reference', 'metric': 'NAR train interactions/sec', 'value': v, 'unit': 'interactions/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec_per_step * 1e3,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(pb, args, gb),
+            'cpu_baseline': {'value': v, 'unit': 'interactions/s', 'cores': cores, 'kind': 'port',
+                             'sample': '%d full train steps of the same global batch (%d sessions) on the torch-CPU oracle; '
+                                       'TF1.12 itself cannot be installed (python 3.12, no network)' % (args.steps, gb)},
+            'e2e': {'value': v, 'unit': 'interactions/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(pb, args, gb):
+    hp = pb.hp
+    return {'workload': 'G1-shaped synthetic' if args.workload == 'g1' else args.workload, 'items': pb.plan.num_items,
+            'acr_dim': pb.plan.acr_dim, 'rnn_units': hp.rnn_units, 'CAR_embedding_size': hp.CAR_embedding_size,
+            'global_batch_sessions': gb, 'per_gpu_batch_sessions': hp.batch_size, 'truncate_session_length': hp.truncate_session_length,
+            'negatives': hp.train_total_negative_samples, 'feature_profile': pb.wl.profile, 'session_len': pb.wl.session_len,
+            'rnn_cell': hp.rnn_cell, 'ranking': hp.ranking, 'parallelism': 'dp%d' % args.gpus,
+            'l2_policy': 'no explicit flush: the per-step working set (X,H1,E,dE,PD activations) exceeds the 126 MB L2'}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from chameleon_recsys_b200 import ops
+    from chameleon_recsys_b200.estimator import build_estimator
+    from chameleon_recsys_b200.harness import make_problem, warm_state
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    pg = None
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        pg = dist.group.WORLD
+    if world != args.gpus:
+        if rank == 0:
+            print('warning: --gpus %d but WORLD_SIZE %d' % (args.gpus, world), file=sys.stderr)
+    pb = make_problem(args.workload, profile=args.profile, session_len=args.session_len)
+    hp = pb.hp
+    gb = hp.batch_size * world
+    warm_state(pb, args.state_warmup)
+    n_total = args.warmup + args.steps
+    # first half: device-resident run, second half: e2e run (the hook starts from the state before batch n_total)
+    batches, state_e2e = make_batches(pb, 2 * n_total, gb, snapshot_at=n_total)
+    est = build_estimator(None, pb.content_article_embeddings_matrix, pb.articles_metadata, pb.articles_features_config,
+                          pb.session_features_config, hp, state_e2e, process_group=pg, device=local_rank)
+    spec = est._ensure_spec(None, None)
+    eng = spec.model.engine
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ value: inputs resident in HBM
+    staged = [eng.stage(f, l, buf, pop, slot='bench%d' % i) for i, (f, l, buf, pop) in enumerate(batches[:n_total])]
+    torch.cuda.synchronize()
+
+    def dev_step(st):
+        eng.grads.zero_()
+        eng.step(st, train=True)
+        eng.apply_gradients()
+
+    for st in staged[:args.warmup]:
+        dev_step(st)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ops.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for st in staged[args.warmup:]:
+        dev_step(st)
+    e1.record()
+    barrier()
+    launches = ops.LAUNCHES - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], device='cuda')
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    n_int = sum(st['L_global'] for st in staged[args.warmup:])
+    value = n_int / (ms_total * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ------------------------------------------------------------------ e2e: Estimator API, host batches
+    e2e_batches = batches[n_total:]
+    h2d = []
+
+    class ListInput:
+        def __init__(self, items):
+            self.items = list(items)
+
+        def get_next(self):
+            from chameleon_recsys_b200.datasets import OutOfRangeError
+            if not self.items:
+                raise OutOfRangeError()
+            f, l, _, _ = self.items.pop(0)
+            return f, l
+
+    est.train(lambda: ListInput(e2e_batches[:args.warmup]))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    e0.record()
+    before_int = est.interactions
+    est.train(lambda: ListInput(e2e_batches[args.warmup:]))
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device='cuda')
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_int = est.interactions - before_int
+    e2e_value = e2e_int / (float(ms2.item()) * 1e-3)
+    h2d_bytes = int(np.mean([s['h2d_bytes'] for s in staged]))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ------------------------------------------------------------------ rooflines (rank 0, kernels timed alone)
+    hbm_peak, tf_peak, tf_sust, peak_src = _peaks()
+    st = staged[-1]
+    roof, roof_g = kernel_rooflines(eng, st, hbm_peak, tf_peak, peak_src)
+
+    # ------------------------------------------------------------------ cpu baseline (bounded sample)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        nb = max(1, args.cpu_steps)
+        v, sec, cores = time_oracle(pb, batches[:nb + 1], 1, nb)
+        cpu = {'value': v, 'unit': 'interactions/s', 'cores': cores, 'kind': 'port',
+               'sample': '%d full train steps (batch %d sessions, %.2f s/step) on the torch-CPU oracle after 1 warm-up; '
+                         'the oracle computes every padded position like the TF graph does' % (nb, gb, sec)}
+
+    line = {'metric': 'NAR train interactions/sec', 'value': value, 'unit': 'interactions/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (tcgen05 kind::tf32: 3xTF32 forward, TF32 backward; fp32 accumulate)',
+            'data': 'synthetic', 'config': workload_config(pb, args, gb),
+            'interactions_per_step': n_int / args.steps,
+            'e2e': {'value': e2e_value, 'unit': 'interactions/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 16,
+                    'ms_per_step': float(ms2.item()) / args.steps, 'wall_ms_per_step': wall * 1e3 / args.steps,
+                    'api': 'Estimator.train(input_fn) -> nar_module_model_fn -> NARModuleModel.train + ItemsStateUpdaterHook'},
+            'gpu_launches': launches, 'gpu_launches_per_step': launches / args.steps,
+            'roofline': roof, 'roofline_gather': roof_g, 'clocks': clocks}
+    if cpu:
+        line['cpu_baseline'] = cpu
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def kernel_rooflines(eng, st, hbm_peak, tf_peak, peak_src):
+    """Time the two kernels north_star names, alone, with CUDA events on the launching stream."""
+    import torch
+    from chameleon_recsys_b200 import ops
+    from chameleon_recsys_b200._lib import ACT_TANH
+    eng.grads.zero_()
+    eng.step(st, train=False, keep=True)
+    L, K = st['L'], eng.K
+    R = L + L * (K + 1)
+    plan = eng.plan
+    planc = eng._plan_c(st)
+    t = st['t']
+    X = eng._buf('X', R, plan.Fp)
+    row_pos, row_item = eng.last['row_pos'], eng.last['row_item']
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')
+
+    def timeit(fn, iters=20):
+        ts = []
+        for _ in range(3):
+            fn()
+        for _ in range(iters):
+            flush.zero_()                         # L2 flush between timed iterations
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.mean(ts))
+
+    ms_g = timeit(lambda: ops.gather_features(planc, row_pos, row_item, R, L, K + 1, t['event_ts'], t['max_ts'], X))
+    E = plan.acr_dim if plan.use_acr else 0
+    Di = plan.item_emb_dim if plan.use_item_emb else 0
+    # per interaction (2+K)*(E+Di)*4 read + same written + (2+K)*8 index bytes
+    gbytes = L * ((2 + K) * (E + Di) * 4 * 2 + (2 + K) * 8)
+    actual = R * plan.Fp * 4 + R * (E + Di) * 4 + R * 12
+    roof_g = {'kernel': 'gather_features_kernel', 'bound': 'hbm', 'achieved': gbytes / (ms_g * 1e-3) / 1e9, 'peak': hbm_peak,
+              'unit': 'GB/s', 'frac': gbytes / (ms_g * 1e-3) / 1e9 / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+              'rows': R, 'us': ms_g * 1e3, 'algorithmic_bytes': gbytes, 'bytes_moved_incl_all_feature_columns': actual,
+              'achieved_incl_all_columns': actual / (ms_g * 1e-3) / 1e9,
+              'note': 'L2 flushed between iterations; the 46 MB ACR + item tables are L2-resident in steady state'}
+    # dominant kernel: CAR layer 2 forward GEMM [R,C]x[C,C], 3xTF32
+    H1 = eng._buf('H1', R, eng.C); Eb = eng._buf('E', R, eng.C)
+    ms_m = timeit(lambda: eng._fwd(H1, 'W2', 'b2', Eb, R, ACT_TANH), iters=10)
+    flops = 2.0 * R * eng.C * eng.C
+    old = eng.fwd_prec
+    eng.fwd_prec = 1
+    ms_m1 = timeit(lambda: eng._fwd(H1, 'W2', 'b2', Eb, R, ACT_TANH), iters=10)
+    eng.fwd_prec = old
+    roof = {'kernel': 'gemm_tf32_kernel<A K-major, B MN-major, 3xTF32> (CAR_representation forward)', 'bound': 'tensor',
+            'achieved': flops / (ms_m * 1e-3) / 1e12, 'peak': tf_peak, 'unit': 'TFLOP/s',
+            'frac': flops / (ms_m * 1e-3) / 1e12 / tf_peak, 'traffic': None, 'peak_source': peak_src + ' cuBLAS bf16 (burst)',
+            'shape': [R, eng.C, eng.C], 'us': ms_m * 1e3,
+            'note': 'algorithmic fp32 FLOPs; the kernel issues 3 tf32 MMAs per FLOP (error-compensated), tf32 peak is '
+                    'half the bf16 peak, so the issued-MMA fraction of the tf32 roofline is 6x this frac',
+            'tf32_single_pass': {'achieved': flops / (ms_m1 * 1e-3) / 1e12, 'us': ms_m1 * 1e3,
+                                 'frac_of_bf16_peak': flops / (ms_m1 * 1e-3) / 1e12 / tf_peak}}
+    return roof, roof_g
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='g1')
+    ap.add_argument('--profile', default='B', choices=['A', 'B'])
+    ap.add_argument('--session-len', default='g1', choices=['g1', 'dense'])
+    ap.add_argument('--state-warmup', type=int, default=100)
+    ap.add_argument('--cpu-steps', type=int, default=5)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == 'ours':
+        args.warmup = 3
+    if args.impl == 'reference':
+        if args.steps > 10:
+            args.steps = 10          # bounded: each oracle step is ~1-3 s of CPU work
+        args.warmup = min(args.warmup, 1)
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

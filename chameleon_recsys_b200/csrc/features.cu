@@ -13,17 +13,19 @@ constexpr float MS_PER_DAY = 1000.0f * 60.0f * 60.0f * 24.0f;
 
 // nar_model.py:1055-1060 (int64 -> float32 BEFORE the subtraction) + log_1p :28-34
 __device__ __forceinline__ float recency_raw(int64_t ts_ref, int64_t created, float inv_log_base) {
-  const float days = fmaxf((__ll2float_rn(ts_ref) - __ll2float_rn(created)) / MS_PER_DAY, 0.f);
-  return logf(days + 1.0f) * inv_log_base;
+  // explicit _rn intrinsics: no FMA contraction, so that the value a row gets is bit-identical to the value
+  // the statistics kernel saw (with degenerate variance, 1 ulp of difference is amplified by 1/1e-12)
+  const float days = fmaxf(__fdiv_rn(__fsub_rn(__ll2float_rn(ts_ref), __ll2float_rn(created)), MS_PER_DAY), 0.f);
+  return __fmul_rn(logf(__fadd_rn(days, 1.0f)), inv_log_base);
 }
 __device__ __forceinline__ float novelty_raw(float pop_norm, float inv_log_base) {
-  return -(logf(pop_norm) * inv_log_base);
+  return -__fmul_rn(logf(pop_norm), inv_log_base);
 }
 // normalize_values + min_max_normalization (:1011-1039, :996-1009); st = {mean, std, zmin, zmax}
 __device__ __forceinline__ float normalize(float x, const float* st) {
-  const float z = (x - st[0]) / st[1];
-  const float scaled = (z - st[2] + 1e-24f) / fmaxf(st[3] - st[2], 2e-24f);
-  return scaled * 2.0f - 1.0f;
+  const float z = __fdiv_rn(__fsub_rn(x, st[0]), st[1]);
+  const float scaled = __fdiv_rn(__fadd_rn(__fsub_rn(z, st[2]), 1e-24f), fmaxf(__fsub_rn(st[3], st[2]), 2e-24f));
+  return __fsub_rn(__fmul_rn(scaled, 2.0f), 1.0f);
 }
 
 __device__ __forceinline__ int row_group(int64_t r, int64_t n_input, int64_t n_cand) {

@@ -116,6 +116,10 @@ class NarEngine:
                 'adam_v': self.layout.to_logical(self.adam_v.cpu().numpy()),
                 'global_step': self.global_step}
 
+    def load_logical_state(self, params, adam_m, adam_v, global_step: int):
+        """Set weights + Adam slots from logical (TF-shaped) dicts, e.g. to start a parity step from a given state."""
+        self.load_state_dict({'params': params, 'adam_m': adam_m, 'adam_v': adam_v, 'global_step': global_step})
+
     def load_state_dict(self, sd: dict):
         self.params.copy_(torch.from_numpy(self.layout.to_internal(sd['params'])))
         self.adam_m.copy_(torch.from_numpy(self.layout.to_internal(sd['adam_m'])))
@@ -141,7 +145,7 @@ class NarEngine:
 
     # ------------------------------------------------------------------ staging (host -> HBM, one copy)
     def stage(self, features: Dict[str, np.ndarray], labels: Dict[str, np.ndarray], buffer: np.ndarray,
-              pop_norm: np.ndarray) -> dict:
+              pop_norm: np.ndarray, slot: str = 'stage') -> dict:
         """Pack the step inputs into one pinned buffer and issue one async H2D copy.
         ``features``/``labels`` hold the GLOBAL batch (all data-parallel ranks see the same arrays)."""
         item_clicked = np.ascontiguousarray(features['item_clicked'], dtype=np.int64)
@@ -181,12 +185,12 @@ class NarEngine:
             offs[name] = (off, arr.size, dt, arr.shape)
             off += arr.size * np.dtype(dt).itemsize
         total = round_up(off, 16)
-        pin = self._pin('stage', total)
+        pin = self._pin(slot, total)
         pin_np = pin.numpy()
         for name, arr, dt in parts:
             o, nel, _, _ = offs[name]
             pin_np[o:o + nel * np.dtype(dt).itemsize].view(dt)[:] = arr.reshape(-1)
-        dev = self._buf('stage', total, 1, torch.uint8).view(-1)
+        dev = self._buf(slot, total, 1, torch.uint8).view(-1)
         dev[:total].copy_(pin[:total], non_blocking=True)
         tmap = {np.int64: torch.int64, np.float32: torch.float32, np.int32: torch.int32}
         tens = {}
@@ -341,8 +345,9 @@ class NarEngine:
                 ops.l2_loss_add(self.params, self.layout.reg_end, self.reg, self.loss_dev[1:2])
         out.update(loss=self.loss_dev, logits=logits)
         if keep:
-            self.last = dict(X=X, H1=H1, E=E, HO=HO, F1=F1, PR=PR, logits=logits, row_pos=row_pos, row_item=row_item,
-                             stats=self.stats, neg=neg_local)
+            # X and H1 are overwritten in place by the backward pass: keep copies for the parity tests
+            self.last = dict(X=X.clone(), H1=H1.clone(), E=E, HO=HO, F1=F1, PR=PR, logits=logits, row_pos=row_pos,
+                             row_item=row_item, stats=self.stats.clone(), neg=neg_local)
         if not train:
             return out
         # =================================================================== backward

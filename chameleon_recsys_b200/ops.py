@@ -11,6 +11,7 @@ from . import _lib
 from ._lib import ACT_LEAKY, ACT_NONE, ACT_TANH, Context, FeaturePlanC, GemmEpilogue, NarError, check
 
 _ctx: dict = {}
+LAUNCHES = 0          # kernels launched through this module (gpu_launches in bench.py)
 
 
 def context(device: Optional[int] = None) -> Context:
@@ -38,6 +39,8 @@ def _chk_f32(*ts):
 def gemm(A: torch.Tensor, B: torch.Tensor, D: torch.Tensor, M: int, N: int, K: int, *, a_kmajor=True, b_kmajor=True,
          lda=None, ldb=None, ldd=None, bias=None, act=ACT_NONE, dact=ACT_NONE, aux=None, ld_aux=None,
          accumulate=False, split_k=1, precision=3):
+    global LAUNCHES
+    LAUNCHES += 1
     """D[M,N] = epilogue(sum_k A(m,k) B(n,k)); see nar_gemm_tf32."""
     _chk_f32(A, B, D, bias, aux)
     lda = A.stride(0) if lda is None else lda
@@ -51,6 +54,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, D: torch.Tensor, M: int, N: int, K: i
 
 
 def gather_rows(table: torch.Tensor, ids: torch.Tensor, out: torch.Tensor, width: int):
+    global LAUNCHES
+    LAUNCHES += 1
     _chk_f32(table, out)
     assert ids.dtype == torch.int64
     lib = _lib.load()
@@ -59,6 +64,8 @@ def gather_rows(table: torch.Tensor, ids: torch.Tensor, out: torch.Tensor, width
 
 
 def scatter_add_rows(table: torch.Tensor, ids: torch.Tensor, src: torch.Tensor, width: int):
+    global LAUNCHES
+    LAUNCHES += 1
     _chk_f32(table, src)
     lib = _lib.load()
     check(lib.nar_scatter_add_rows_f32(_p(table), table.shape[0], table.stride(0), width, _p(ids), ids.numel(), _p(src),
@@ -66,12 +73,16 @@ def scatter_add_rows(table: torch.Tensor, ids: torch.Tensor, src: torch.Tensor, 
 
 
 def gather_features(plan: FeaturePlanC, row_pos, row_item, n_rows, n_input, n_cand, event_ts, max_ts, out):
+    global LAUNCHES
+    LAUNCHES += 1
     ctx = context()
     check(ctx.lib.nar_gather_features(ctx.handle, C.byref(plan), _p(row_pos), _p(row_item), n_rows, n_input, n_cand,
                                       _p(event_ts), _p(max_ts), _p(out), _stream()), 'nar_gather_features')
 
 
 def gather_features_bwd(plan: FeaturePlanC, row_pos, row_item, n_rows, n_input, n_cand, event_ts, max_ts, d_out, d_gamma, d_beta):
+    global LAUNCHES
+    LAUNCHES += 1
     ctx = context()
     check(ctx.lib.nar_gather_features_bwd(ctx.handle, C.byref(plan), _p(row_pos), _p(row_item), n_rows, n_input, n_cand,
                                           _p(event_ts), _p(max_ts), _p(d_out), _p(d_gamma), _p(d_beta), _stream()),
@@ -79,12 +90,16 @@ def gather_features_bwd(plan: FeaturePlanC, row_pos, row_item, n_rows, n_input, 
 
 
 def build_rows(pos_idx, L, item_clicked, label_next, negatives, K, row_pos, row_item):
+    global LAUNCHES
+    LAUNCHES += 1
     check(_lib.load().nar_build_rows(_p(pos_idx), L, _p(item_clicked), _p(label_next), _p(negatives), K, _p(row_pos),
                                      _p(row_item), _stream()), 'nar_build_rows')
 
 
 def feature_stats(buffer, n_norm, created_at_ts, pop_norm, max_ts, log_base_rec, log_base_nov, row_pos, row_item,
                   n_rows, n_input, n_cand, event_ts, stats):
+    global LAUNCHES
+    LAUNCHES += 1
     ctx = context()
     check(ctx.lib.nar_feature_stats(ctx.handle, _p(buffer), buffer.numel(), n_norm, _p(created_at_ts), _p(pop_norm),
                                     _p(max_ts), log_base_rec, log_base_nov, _p(row_pos), _p(row_item), n_rows, n_input,
@@ -92,12 +107,16 @@ def feature_stats(buffer, n_norm, created_at_ts, pop_norm, max_ts, log_base_rec,
 
 
 def ugrnn_fwd(gx, Wh, sess_off, B, Hp, h_out, gate, cand):
+    global LAUNCHES
+    LAUNCHES += 1
     ctx = context()
     check(ctx.lib.nar_ugrnn_fwd(ctx.handle, _p(gx), _p(Wh), _p(sess_off), B, Hp, _p(h_out), _p(gate), _p(cand), _stream()),
           'nar_ugrnn_fwd')
 
 
 def ugrnn_bwd(d_hout, h_out, gate, cand, WhT, sess_off, B, Hp, d_gx, h_prev):
+    global LAUNCHES
+    LAUNCHES += 1
     ctx = context()
     check(ctx.lib.nar_ugrnn_bwd(ctx.handle, _p(d_hout), _p(h_out), _p(gate), _p(cand), _p(WhT), _p(sess_off), B, Hp,
                                 _p(d_gx), _p(h_prev), _stream()), 'nar_ugrnn_bwd')
@@ -111,6 +130,8 @@ def sample_negatives_workspace(Bg, T1, buf_len, K) -> int:
 
 
 def sample_negatives(all_items_global, sess0, B, buffer, K, n_from_buffer, seed, step, out, workspace):
+    global LAUNCHES
+    LAUNCHES += 2 if B > 0 else 1
     ctx = context()
     Bg, T1 = all_items_global.shape
     check(ctx.lib.nar_sample_negatives(ctx.handle, _p(all_items_global), Bg, T1, sess0, B, _p(buffer), buffer.numel(), K,
@@ -120,41 +141,59 @@ def sample_negatives(all_items_global, sess0, B, buffer, K, n_from_buffer, seed,
 
 
 def mul_pred(cand, pred, n_pos, n_cand, Cdim, prod):
+    global LAUNCHES
+    LAUNCHES += 1
     check(_lib.load().nar_mul_pred(_p(cand), _p(pred), n_pos, n_cand, Cdim, _p(prod), _stream()), 'nar_mul_pred')
 
 
 def mul_pred_bwd(d_prod, cand, pred, n_pos, n_cand, Cdim, d_cand, d_pred):
+    global LAUNCHES
+    LAUNCHES += 1
     check(_lib.load().nar_mul_pred_bwd(_p(d_prod), _p(cand), _p(pred), n_pos, n_cand, Cdim, _p(d_cand), _p(d_pred), _stream()),
           'nar_mul_pred_bwd')
 
 
 def score_softmax_ce(z3, ld_z, width, m4, ld_m4, c4, n_pos, n_cand, inv_temp, inv_count, logits, loss_sum, d_z3, d_m4, d_c4):
+    global LAUNCHES
+    LAUNCHES += 1
     check(_lib.load().nar_score_softmax_ce(_p(z3), ld_z, width, _p(m4), ld_m4, _p(c4), n_pos, n_cand, inv_temp, inv_count,
                                            _p(logits), _p(loss_sum), _p(d_z3), _p(d_m4), _p(d_c4), _stream()),
           'nar_score_softmax_ce')
 
 
 def cosine_softmax_ce(cand, pred, n_pos, n_cand, Cdim, inv_temp, inv_count, logits, loss_sum, d_cand, d_pred):
+    global LAUNCHES
+    LAUNCHES += 1
     check(_lib.load().nar_cosine_softmax_ce(_p(cand), _p(pred), n_pos, n_cand, Cdim, inv_temp, inv_count, _p(logits),
                                             _p(loss_sum), _p(d_cand), _p(d_pred), _stream()), 'nar_cosine_softmax_ce')
 
 
 def colsum_add(x, rows, cols, ld, out):
+    global LAUNCHES
+    LAUNCHES += 1
     check(_lib.load().nar_colsum_add(_p(x), rows, cols, ld, _p(out), _stream()), 'nar_colsum_add')
 
 
 def act_bwd(dy, y, n, act, dx):
+    global LAUNCHES
+    LAUNCHES += 1
     check(_lib.load().nar_act_bwd(_p(dy), _p(y), n, act, _p(dx), _stream()), 'nar_act_bwd')
 
 
 def l2_loss_add(x, n, scale, out):
+    global LAUNCHES
+    LAUNCHES += 1
     check(_lib.load().nar_l2_loss_add(_p(x), n, scale, _p(out), _stream()), 'nar_l2_loss_add')
 
 
 def transpose(src, rows, cols, ld_src, dst, ld_dst):
+    global LAUNCHES
+    LAUNCHES += 1
     check(_lib.load().nar_transpose_f32(_p(src), rows, cols, ld_src, _p(dst), ld_dst, _stream()), 'nar_transpose_f32')
 
 
 def adam_tf(params, grads, m, v, n, reg_end, reg_l2, lr, step, beta1=0.9, beta2=0.999, eps=1e-8):
+    global LAUNCHES
+    LAUNCHES += 1
     check(_lib.load().nar_adam_tf(_p(params), _p(grads), _p(m), _p(v), n, reg_end, reg_l2, lr, beta1, beta2, eps, step,
                                   _stream()), 'nar_adam_tf')

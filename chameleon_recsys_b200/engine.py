@@ -27,6 +27,7 @@ import torch
 
 from . import ops
 from ._lib import ACT_LEAKY, ACT_NONE, ACT_TANH, FeaturePlanC, NarError
+from .dp import shard_sessions
 from .plan import (SEG_ACR, SEG_CTX_EMBED, SEG_ITEM_EMB, SEG_META_EMBED, FeaturePlan, ParamLayout, round_up)
 
 
@@ -150,21 +151,10 @@ class NarEngine:
         ``features``/``labels`` hold the GLOBAL batch (all data-parallel ranks see the same arrays)."""
         item_clicked = np.ascontiguousarray(features['item_clicked'], dtype=np.int64)
         Bg, T = item_clicked.shape
-        lens_g = np.clip(np.asarray(features['session_size'], dtype=np.int64) - 1, 0, T)
-        L_global = int(lens_g.sum())
-        per = Bg // self.world
-        if per * self.world != Bg:
-            raise ValueError('global batch %d not divisible by world size %d' % (Bg, self.world))
-        s0 = self.rank * per
-        lens = lens_g[s0:s0 + per]
-        L = int(lens.sum())
-        sess_off = np.zeros(per + 1, dtype=np.int32)
-        np.cumsum(lens, out=sess_off[1:])
-        # compact valid positions, session-major: flat index into the GLOBAL [Bg*T] arrays
-        tt = np.arange(T, dtype=np.int64)[None, :]
-        valid = tt < lens[:, None]
-        bb = (np.arange(per, dtype=np.int64) + s0)[:, None]
-        pos_idx = (bb * T + tt)[valid].astype(np.int32)
+        # this rank's sessions + compact valid positions (session-major; flat index into the GLOBAL [Bg*T] arrays)
+        sh = shard_sessions(np.asarray(features['session_size']), T, self.world, self.rank)
+        s0, per, lens, L, L_global = sh['s0'], sh['per'], sh['lens'], sh['L'], sh['L_global']
+        sess_off, pos_idx = sh['sess_off'], sh['pos_idx']
         all_items = np.concatenate([item_clicked, np.asarray(labels['label_last_item'], dtype=np.int64).reshape(Bg, 1)], axis=1)
         ev = np.ascontiguousarray(features['event_timestamp'], dtype=np.int64)
         parts = [('all_items', all_items, np.int64), ('event_ts', ev, np.int64),

@@ -136,7 +136,9 @@ def time_oracle(pb, batches, warmup, steps):
     """Reference CPU path: full train step (sampler + fwd + bwd + TF-Adam + host state is pre-applied) per batch."""
     import torch
     from oracle import sampler_ref
-    torch.set_num_threads(os.cpu_count() or 1)
+    # measured on the GPU box (128 logical CPUs): 8 -> 148, 16 -> 185, 32 -> 177, 64 -> 134, 128 -> 10 interactions/s;
+    # more threads than ~16 only add synchronisation cost to these GEMM sizes, so the baseline runs at its best setting
+    torch.set_num_threads(min(os.cpu_count() or 1, int(os.environ.get('NAR_CPU_THREADS', '16'))))
     hp = pb.hp
     o = oracle_for(pb)
     n_int, t_total = 0, 0.0

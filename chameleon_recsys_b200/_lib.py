@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, 'libnar_b200.so')
 
 NAR_MAX_SEGMENTS = 24
 NAR_MAX_SRC = 16
+NAR_MAX_COLS = 1024
 
 ACT_NONE, ACT_LEAKY, ACT_TANH = 0, 1, 2
 
@@ -32,7 +33,9 @@ class FeaturePlanC(C.Structure):
                 ('meta', C.c_void_p * NAR_MAX_SRC),
                 ('created_at_ts', C.c_void_p), ('pop_norm', C.c_void_p),
                 ('gamma', C.c_void_p), ('beta', C.c_void_p), ('stats', C.c_void_p),
-                ('log_base_recency', C.c_float), ('log_base_novelty', C.c_float)]
+                ('log_base_recency', C.c_float), ('log_base_novelty', C.c_float),
+                ('n_narrow', C.c_int32), ('narrow_begin', C.c_int32 * 4), ('narrow_end', C.c_int32 * 4),
+                ('col_seg', C.c_uint8 * NAR_MAX_COLS)]
 
 
 class GemmEpilogue(C.Structure):

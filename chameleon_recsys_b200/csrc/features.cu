@@ -78,43 +78,41 @@ gather_features_kernel(const __grid_constant__ nar_feature_plan P, const int32_t
   const int64_t ts_ref = (r < n_input) ? event_ts[pos] : max_ts[0];
   const float* st = P.stats + 8 * row_group(r, n_input, n_cand);
   float* orow = out + r * (int64_t)P.row_ld;
-  int written_end = 0;
+  // 1) wide table rows (ACR, item embedding): all loads issued before the narrow columns' dependent chains
   for (int s = 0; s < P.n_segments; ++s) {
     const nar_segment& sg = P.seg[s];
-    const int end = sg.col + sg.width;
-    written_end = end > written_end ? end : written_end;
-    if (sg.kind == NAR_SEG_ACR || sg.kind == NAR_SEG_ITEM_EMB) {
-      const float* src = sg.table + item * (int64_t)sg.ld;
-      const bool vec = ((sg.col & 3) == 0) && ((sg.ld & 3) == 0) && ((P.row_ld & 3) == 0);
-      int j0 = 0;
-      if (vec) {
-        const int nv = sg.width >> 2;
-        const float4* s4 = reinterpret_cast<const float4*>(src);
-        const float4* g4 = reinterpret_cast<const float4*>(P.gamma + sg.col);
-        const float4* b4 = reinterpret_cast<const float4*>(P.beta + sg.col);
-        float4* o4 = reinterpret_cast<float4*>(orow + sg.col);
-        for (int j = lane; j < nv; j += 32) {
-          float4 v = __ldg(s4 + j);
-          const float4 g = __ldg(g4 + j), b = __ldg(b4 + j);
-          v.x = v.x * g.x + b.x; v.y = v.y * g.y + b.y; v.z = v.z * g.z + b.z; v.w = v.w * g.w + b.w;
-          o4[j] = v;
-        }
-        j0 = nv << 2;
+    if (sg.kind != NAR_SEG_ACR && sg.kind != NAR_SEG_ITEM_EMB) continue;
+    const float* src = sg.table + item * (int64_t)sg.ld;
+    const bool vec = ((sg.col & 3) == 0) && ((sg.ld & 3) == 0) && ((P.row_ld & 3) == 0);
+    int j0 = 0;
+    if (vec) {
+      const int nv = sg.width >> 2;
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      const float4* g4 = reinterpret_cast<const float4*>(P.gamma + sg.col);
+      const float4* b4 = reinterpret_cast<const float4*>(P.beta + sg.col);
+      float4* o4 = reinterpret_cast<float4*>(orow + sg.col);
+      for (int j = lane; j < nv; j += 32) {
+        float4 v = __ldg(s4 + j);
+        const float4 g = __ldg(g4 + j), b = __ldg(b4 + j);
+        v.x = v.x * g.x + b.x; v.y = v.y * g.y + b.y; v.z = v.z * g.z + b.z; v.w = v.w * g.w + b.w;
+        __stcs(o4 + j, v);                          // streaming store: the row is consumed once by the GEMM's TMA
       }
-      for (int j = j0 + lane; j < sg.width; j += 32)
-        orow[sg.col + j] = __ldg(src + j) * P.gamma[sg.col + j] + P.beta[sg.col + j];
-    } else {
-      for (int j = lane; j < sg.width; j += 32) {
-        const int c = sg.col + j;
-        orow[c] = seg_value(P, sg, j, pos, item, ts_ref, st) * P.gamma[c] + P.beta[c];
-      }
+      j0 = nv << 2;
     }
+    for (int j = j0 + lane; j < sg.width; j += 32)
+      orow[sg.col + j] = __ldg(src + j) * P.gamma[sg.col + j] + P.beta[sg.col + j];
   }
-  // padding columns (alignment gaps are covered too: anything not owned by a segment is zero)
-  for (int c = lane; c < P.row_ld; c += 32) {
-    bool owned = false;
-    for (int s = 0; s < P.n_segments; ++s) owned |= (c >= P.seg[s].col && c < P.seg[s].col + P.seg[s].width);
-    if (!owned) orow[c] = 0.f;
+  // 2) narrow columns (one-hot, small embeddings, numerics, recency, novelty, padding): one lane per column
+  for (int q = 0; q < P.n_narrow; ++q) {
+    for (int c = P.narrow_begin[q] + lane; c < P.narrow_end[q]; c += 32) {
+      const int si = P.col_seg[c];
+      float v = 0.f;
+      if (si != 255) {
+        const nar_segment& sg = P.seg[si];
+        v = seg_value(P, sg, c - sg.col, pos, item, ts_ref, st) * P.gamma[c] + P.beta[c];
+      }
+      orow[c] = v;
+    }
   }
 }
 
@@ -143,10 +141,8 @@ gather_features_bwd_kernel(const __grid_constant__ nar_feature_plan P, const int
   }
   __syncthreads();
   for (int c = threadIdx.x; c < P.row_ld; c += BWD_THREADS) {
-    int si = -1;
-    for (int s = 0; s < P.n_segments; ++s)
-      if (c >= P.seg[s].col && c < P.seg[s].col + P.seg[s].width) si = s;
-    if (si < 0) continue;
+    const int si = P.col_seg[c];
+    if (si == 255) continue;
     const nar_segment& sg = P.seg[si];
     const int j = c - sg.col;
     const float gam = P.gamma[c];

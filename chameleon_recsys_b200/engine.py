@@ -89,15 +89,22 @@ class NarEngine:
         self._bufs: Dict[str, torch.Tensor] = {}
         self._pinned: Dict[str, torch.Tensor] = {}
         self._sampler_ws = None
+        self._planc_static = None
+        self._views: dict = {}
         self.last: Dict[str, torch.Tensor] = {}
         self.ops = ops
         ops.context(self.dev.index)     # fail loudly here if the library / device is unusable
 
     # ------------------------------------------------------------------ parameters
     def view(self, key: str, buf: Optional[torch.Tensor] = None) -> torch.Tensor:
-        t = self.layout.by_key[key]
         b = self.params if buf is None else buf
-        return b[t.offset:t.offset + t.size].view(t.rows, t.ld)
+        ck = (key, b.data_ptr())
+        v = self._views.get(ck)
+        if v is None:
+            t = self.layout.by_key[key]
+            v = b[t.offset:t.offset + t.size].view(t.rows, t.ld)
+            self._views[ck] = v
+        return v
 
     def set_params(self, logical: Dict[str, np.ndarray]):
         flat = self.layout.to_internal(logical)
@@ -192,11 +199,23 @@ class NarEngine:
 
     # ------------------------------------------------------------------ feature plan for this step
     def _plan_c(self, st: dict) -> FeaturePlanC:
+        """Per-step plan = cached static part (tables, column map) + this step's staged input pointers."""
+        if self._planc_static is None:
+            self._planc_static = bytes(self._plan_c_static())
+        p = FeaturePlanC.from_buffer_copy(self._planc_static)
+        t = st['t']
+        for i, n in enumerate(self.plan.ctx_int_names):
+            p.ctx_int[i] = t['ci/' + n].data_ptr()
+        for i, n in enumerate(self.plan.ctx_float_names):
+            p.ctx_float[i] = t['cf/' + n].data_ptr()
+        p.pop_norm = t['pop_norm'].data_ptr()
+        return p
+
+    def _plan_c_static(self) -> FeaturePlanC:
         p = FeaturePlanC()
         pl = self.plan
         p.n_segments = len(pl.segments)
         p.row_ld = pl.Fp
-        t = st['t']
         for i, s in enumerate(pl.segments):
             sg = p.seg[i]
             sg.kind, sg.col, sg.width, sg.card, sg.src = s.kind, s.int_col, s.width, s.card, s.src
@@ -208,18 +227,30 @@ class NarEngine:
                 sg.ld = pt.ld
                 sg.table = self.params.data_ptr() + 4 * pt.offset
                 sg.grad = self.grads.data_ptr() + 4 * pt.offset
-        for i, n in enumerate(pl.ctx_int_names):
-            p.ctx_int[i] = t['ci/' + n].data_ptr()
-        for i, n in enumerate(pl.ctx_float_names):
-            p.ctx_float[i] = t['cf/' + n].data_ptr()
         for i, m in enumerate(self.meta):
             p.meta[i] = m.data_ptr()
         p.created_at_ts = self.created_at.data_ptr()
-        p.pop_norm = t['pop_norm'].data_ptr()
         p.gamma = self.view('gamma').data_ptr()
         p.beta = self.view('beta').data_ptr()
         p.stats = self.stats.data_ptr()
         p.log_base_recency, p.log_base_novelty = self.lb_rec, self.lb_nov
+        # column -> segment map and the column ranges outside the wide (vector-copied) segments
+        if pl.Fp > len(p.col_seg):
+            raise NarError('feature rows wider than NAR_MAX_COLS')
+        cs = np.full(len(p.col_seg), 255, dtype=np.uint8)
+        wide = np.zeros(pl.Fp, dtype=bool)
+        for i, s in enumerate(pl.segments):
+            cs[s.int_col:s.int_col + s.width] = i
+            if s.kind in (SEG_ACR, SEG_ITEM_EMB):
+                wide[s.int_col:s.int_col + s.width] = True
+        C.memmove(p.col_seg, cs.ctypes.data, len(p.col_seg))
+        edges = np.flatnonzero(np.diff(np.concatenate([[True], wide, [True]]).astype(np.int8)))
+        ranges = list(zip(edges[0::2], edges[1::2]))
+        if len(ranges) > 4:
+            raise NarError('more than 4 narrow column ranges')
+        p.n_narrow = len(ranges)
+        for i, (a, b) in enumerate(ranges):
+            p.narrow_begin[i], p.narrow_end[i] = int(a), int(b)
         return p
 
     # ------------------------------------------------------------------ GEMM helpers

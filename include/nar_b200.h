@@ -65,6 +65,7 @@ typedef struct {
 
 #define NAR_MAX_SEGMENTS 24
 #define NAR_MAX_SRC 16
+#define NAR_MAX_COLS 1024
 
 typedef struct {
   int32_t n_segments;
@@ -80,6 +81,12 @@ typedef struct {
   const float*   stats;                 /* [3][8] normalisation stats (input / positive / negative rows), see nar_feature_stats */
   float log_base_recency;               /* elapsed_days_smooth_log_base */
   float log_base_novelty;               /* popularity_smooth_log_base */
+  /* column map: col_seg[c] = index into seg[] of the segment that owns output column c, 255 = padding.
+   * narrow_begin/end: the column ranges NOT covered by the wide (ACR / item-embedding) segments. */
+  int32_t n_narrow;
+  int32_t narrow_begin[4];
+  int32_t narrow_end[4];
+  uint8_t col_seg[NAR_MAX_COLS];
 } nar_feature_plan;
 
 /* rows: row_pos[r] = flat index b*T+t of the position that owns row r (context features,

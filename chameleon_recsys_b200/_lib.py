@@ -41,7 +41,7 @@ class FeaturePlanC(C.Structure):
 class GemmEpilogue(C.Structure):
     _fields_ = [('bias', C.c_void_p), ('act', C.c_int32), ('dact', C.c_int32), ('aux', C.c_void_p),
                 ('ld_aux', C.c_int64), ('accumulate', C.c_int32), ('split_k', C.c_int32),
-                ('precision', C.c_int32)]
+                ('precision', C.c_int32), ('b_lo', C.c_void_p)]
 
 
 _lib: Optional[C.CDLL] = None
@@ -73,7 +73,8 @@ _SIGNATURES = {
     'nar_act_bwd': (C.c_int, [vp, vp, i64, C.c_int, vp, vp]),
     'nar_l2_loss_add': (C.c_int, [vp, i64, f32, vp, vp]),
     'nar_transpose_f32': (C.c_int, [vp, i64, i64, i64, vp, i64, vp]),
-    'nar_adam_tf': (C.c_int, [vp, vp, vp, vp, i64, i64, f32, f32, f32, f32, f32, i64, vp]),
+    'nar_adam_tf': (C.c_int, [vp, vp, vp, vp, i64, i64, f32, f32, f32, f32, f32, i64, vp, vp]),
+    'nar_tf32_lo': (C.c_int, [vp, i64, vp, vp]),
 }
 
 EXPORTED_SYMBOLS = sorted(_SIGNATURES.keys())

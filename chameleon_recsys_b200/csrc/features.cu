@@ -62,31 +62,58 @@ __device__ __forceinline__ float seg_value(const nar_feature_plan& P, const nar_
 }
 
 // ------------------------------------------------------------------ forward gather
-// one warp per output row; wide table segments move as 128-bit loads / stores when aligned
+// One warp per output row.  Design for HBM speed:
+//  * the per-CTA copy of the column map / segment table lives in shared memory (divergent lookups in the
+//    constant bank would serialise 32x);
+//  * phase A: every scalar the row needs (context ids / floats at its position, metadata of its item,
+//    created_at, pop_norm) is fetched by ONE lane each, all independent -> one memory round trip, then
+//    handed to the lanes that need it with warp shuffles (no dependent load chains per column);
+//  * phase B: the wide table rows (ACR, item embedding) move as 128-bit loads / streaming 128-bit stores;
+//  * phase C: narrow columns, one lane per column.
 constexpr int GATHER_WARPS = 8;
+constexpr int LANE_CTX_INT = 0, LANE_CTX_FLOAT = 12, LANE_META = 20, LANE_CREATED = 28, LANE_POP = 29;
+
+struct SegS { int kind, col, card, src, ld; const float* table; };
 
 __global__ void __launch_bounds__(GATHER_WARPS * 32)
-gather_features_kernel(const __grid_constant__ nar_feature_plan P, const int32_t* __restrict__ row_pos,
+gather_features_kernel(const __grid_constant__ nar_feature_plan P, int n_ctx_int, int n_ctx_float, int n_meta,
+                       const int32_t* __restrict__ row_pos,
                        const int64_t* __restrict__ row_item, int64_t n_rows, int64_t n_input, int64_t n_cand,
                        const int64_t* __restrict__ event_ts, const int64_t* __restrict__ max_ts,
                        float* __restrict__ out) {
+  __shared__ uint8_t s_colseg[NAR_MAX_COLS];
+  __shared__ SegS s_seg[NAR_MAX_SEGMENTS];
+  for (int i = threadIdx.x; i < P.row_ld; i += blockDim.x) s_colseg[i] = P.col_seg[i];
+  if (threadIdx.x < P.n_segments) {
+    const nar_segment& g = P.seg[threadIdx.x];
+    s_seg[threadIdx.x] = SegS{g.kind, g.col, g.card, g.src, g.ld, g.table};
+  }
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * GATHER_WARPS + (threadIdx.x >> 5);
   if (r >= n_rows) return;
   const int64_t pos = row_pos[r];
   const int64_t item = row_item[r];
+  // ---- phase A: scalars, one lane each
+  long long mine = 0;
+  if (lane < LANE_CTX_FLOAT) { if (lane < n_ctx_int) mine = P.ctx_int[lane][pos]; }
+  else if (lane < LANE_META) { if (lane - LANE_CTX_FLOAT < n_ctx_float) mine = (long long)__float_as_int(P.ctx_float[lane - LANE_CTX_FLOAT][pos]); }
+  else if (lane < LANE_CREATED) { if (lane - LANE_META < n_meta) mine = P.meta[lane - LANE_META][item]; }
+  else if (lane == LANE_CREATED) mine = P.created_at_ts[item];
+  else if (lane == LANE_POP) mine = (long long)__float_as_int(P.pop_norm[item]);
   const int64_t ts_ref = (r < n_input) ? event_ts[pos] : max_ts[0];
   const float* st = P.stats + 8 * row_group(r, n_input, n_cand);
   float* orow = out + r * (int64_t)P.row_ld;
-  // 1) wide table rows (ACR, item embedding): all loads issued before the narrow columns' dependent chains
+  // ---- phase B: wide table rows
   for (int s = 0; s < P.n_segments; ++s) {
-    const nar_segment& sg = P.seg[s];
+    const SegS sg = s_seg[s];
     if (sg.kind != NAR_SEG_ACR && sg.kind != NAR_SEG_ITEM_EMB) continue;
+    const int width = P.seg[s].width;
     const float* src = sg.table + item * (int64_t)sg.ld;
     const bool vec = ((sg.col & 3) == 0) && ((sg.ld & 3) == 0) && ((P.row_ld & 3) == 0);
     int j0 = 0;
     if (vec) {
-      const int nv = sg.width >> 2;
+      const int nv = width >> 2;
       const float4* s4 = reinterpret_cast<const float4*>(src);
       const float4* g4 = reinterpret_cast<const float4*>(P.gamma + sg.col);
       const float4* b4 = reinterpret_cast<const float4*>(P.beta + sg.col);
@@ -99,17 +126,46 @@ gather_features_kernel(const __grid_constant__ nar_feature_plan P, const int32_t
       }
       j0 = nv << 2;
     }
-    for (int j = j0 + lane; j < sg.width; j += 32)
+    for (int j = j0 + lane; j < width; j += 32)
       orow[sg.col + j] = __ldg(src + j) * P.gamma[sg.col + j] + P.beta[sg.col + j];
   }
-  // 2) narrow columns (one-hot, small embeddings, numerics, recency, novelty, padding): one lane per column
+  // ---- phase C: narrow columns (one-hot, small embeddings, numerics, recency, novelty, padding)
+  const float ilr = 1.0f / logf(P.log_base_recency), iln = 1.0f / logf(P.log_base_novelty);
   for (int q = 0; q < P.n_narrow; ++q) {
-    for (int c = P.narrow_begin[q] + lane; c < P.narrow_end[q]; c += 32) {
-      const int si = P.col_seg[c];
+    const int begin = P.narrow_begin[q], end = P.narrow_end[q];
+    for (int c0 = begin; c0 < end; c0 += 32) {             // warp-uniform trip count (shuffles inside)
+      const int c = c0 + lane;
+      const bool valid = c < end;
+      const int si = valid ? s_colseg[c] : 255;
+      SegS sg = s_seg[si == 255 ? 0 : si];
+      int src_lane = lane;
+      switch (sg.kind) {
+        case NAR_SEG_CTX_OHE: case NAR_SEG_CTX_EMBED: src_lane = LANE_CTX_INT + sg.src; break;
+        case NAR_SEG_CTX_NUM: src_lane = LANE_CTX_FLOAT + sg.src; break;
+        case NAR_SEG_META_OHE: case NAR_SEG_META_EMBED: case NAR_SEG_META_NUM: src_lane = LANE_META + sg.src; break;
+        case NAR_SEG_RECENCY: src_lane = LANE_CREATED; break;
+        case NAR_SEG_NOVELTY: src_lane = LANE_POP; break;
+        default: break;
+      }
+      const long long val = __shfl_sync(0xffffffffu, mine, src_lane);
+      if (!valid) continue;
       float v = 0.f;
       if (si != 255) {
-        const nar_segment& sg = P.seg[si];
-        v = seg_value(P, sg, c - sg.col, pos, item, ts_ref, st) * P.gamma[c] + P.beta[c];
+        const int j = c - sg.col;
+        float raw = 0.f;
+        switch (sg.kind) {
+          case NAR_SEG_CTX_OHE: case NAR_SEG_META_OHE: raw = (val == (long long)j) ? 1.f : 0.f; break;
+          case NAR_SEG_CTX_EMBED: case NAR_SEG_META_EMBED: {
+            const long long id = val < 0 ? 0 : (val >= sg.card ? sg.card - 1 : val);
+            raw = __ldg(sg.table + id * sg.ld + j);
+          } break;
+          case NAR_SEG_CTX_NUM: raw = __int_as_float((int)val); break;
+          case NAR_SEG_META_NUM: raw = (float)val; break;
+          case NAR_SEG_RECENCY: raw = normalize(recency_raw(ts_ref, (int64_t)val, ilr), st); break;
+          case NAR_SEG_NOVELTY: raw = normalize(novelty_raw(__int_as_float((int)val), iln), st + 4); break;
+          default: break;
+        }
+        v = raw * P.gamma[c] + P.beta[c];
       }
       orow[c] = v;
     }
@@ -363,8 +419,17 @@ extern "C" int nar_gather_features(nar_ctx* ctx, const nar_feature_plan* plan, c
   if (plan->n_segments > NAR_MAX_SEGMENTS) return NAR_ERR_INVALID;
   if (n_rows <= 0) return NAR_OK;
   const unsigned grid = (unsigned)((n_rows + nar::feat::GATHER_WARPS - 1) / nar::feat::GATHER_WARPS);
+  // lane budget of the scalar prefetch (phase A): <= 12 context ids, <= 8 context floats, <= 8 metadata arrays
+  int n_ci = 0, n_cf = 0, n_me = 0;
+  for (int i = 0; i < plan->n_segments; ++i) {
+    const nar_segment& g = plan->seg[i];
+    if (g.kind == NAR_SEG_CTX_OHE || g.kind == NAR_SEG_CTX_EMBED) n_ci = g.src + 1 > n_ci ? g.src + 1 : n_ci;
+    if (g.kind == NAR_SEG_CTX_NUM) n_cf = g.src + 1 > n_cf ? g.src + 1 : n_cf;
+    if (g.kind == NAR_SEG_META_OHE || g.kind == NAR_SEG_META_EMBED || g.kind == NAR_SEG_META_NUM) n_me = g.src + 1 > n_me ? g.src + 1 : n_me;
+  }
+  if (n_ci > 12 || n_cf > 8 || n_me > 8 || plan->row_ld > NAR_MAX_COLS) return NAR_ERR_UNSUPPORTED;
   nar::feat::gather_features_kernel<<<grid, nar::feat::GATHER_WARPS * 32, 0, as_stream(stream)>>>(
-      *plan, row_pos, row_item, n_rows, n_input, n_cand, event_timestamp, max_ts, out);
+      *plan, n_ci, n_cf, n_me, row_pos, row_item, n_rows, n_input, n_cand, event_timestamp, max_ts, out);
   NAR_LAUNCH_CHECK();
   return NAR_OK;
 }

@@ -33,10 +33,19 @@ constexpr int TILE_B_BYTES = BN * BK * 4;
 constexpr int NUM_THREADS = 256;
 constexpr int TMEM_COLS = 128;
 
-template <bool SPLIT3> struct Cfg {
-  static constexpr int STAGE_BYTES = (SPLIT3 ? 2 : 1) * (TILE_A_BYTES + TILE_B_BYTES);
-  static constexpr int STAGES = SPLIT3 ? 3 : 6;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;   // tiles + barriers + align slack
+// Two shared-memory rings.  The operand ring (TMA destination, the "hi" tiles) is deep so that TMA latency
+// (~1-2 us from L2/HBM under load) is hidden; the 3xTF32 "lo" tiles only live from the split to the MMA that
+// consumes them, so their ring is shallow.  (One combined hi+lo ring allowed 3 stages and left the 3xTF32 GEMMs
+// TMA-latency bound: measured 37 us per 128x128x1024 tile vs 13 us of MMA time.)
+// BLO: the lo plane of operand B (the weights) is read from HBM by TMA (nar_adam_tf maintains it), so the in-kernel
+// split only touches the A tile: operand stage = A | B | B_lo (48 KB), lo ring = A_lo only (16 KB).
+template <bool SPLIT3, bool BLO> struct Cfg {
+  static constexpr int STAGE_BYTES = TILE_A_BYTES + TILE_B_BYTES * (BLO ? 2 : 1);   // one operand stage (A | B [| B_lo])
+  static constexpr int LO_STAGE_BYTES = SPLIT3 ? (BLO ? TILE_A_BYTES : TILE_A_BYTES + TILE_B_BYTES) : 0;
+  static constexpr int STAGES = SPLIT3 ? (BLO ? 4 : 5) : 6;                 // operand ring depth
+  static constexpr int LO_STAGES = SPLIT3 ? 2 : 0;                          // lo ring depth
+  static constexpr int TILE_BYTES = STAGES * STAGE_BYTES + LO_STAGES * LO_STAGE_BYTES;
+  static constexpr int SMEM_BYTES = TILE_BYTES + 256 + 1024;                // tiles + barriers + align slack
 };
 
 struct Params {
@@ -146,20 +155,24 @@ __device__ __forceinline__ float tf32_lo(float x) {
 }
 
 // ---------------------------------------------------------------- kernel
-template <bool A_MN, bool B_MN, bool SPLIT3>
+template <bool A_MN, bool B_MN, bool SPLIT3, bool BLO>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
-  using C = Cfg<SPLIT3>;
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_blo, const Params p) {
+  using C = Cfg<SPLIT3, BLO>;
+  static_assert(!BLO || SPLIT3, "B_lo only exists in 3xTF32 mode");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* tiles = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + C::STAGES;
-  uint64_t* xf = bars + 2 * C::STAGES;
-  uint64_t* tmem_full = bars + 3 * C::STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * C::STAGES + 1);
+  uint8_t* lo_tiles = smem + C::STAGES * C::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::TILE_BYTES);
+  uint64_t* full = bars;                          // [STAGES]    TMA landed
+  uint64_t* empty = bars + C::STAGES;             // [STAGES]    MMAs that read the operand stage retired
+  uint64_t* xf = bars + 2 * C::STAGES;            // [LO_STAGES] lo tiles written (128 arrivals)
+  uint64_t* lo_empty = xf + 2;                    // [LO_STAGES] MMAs that read the lo stage retired
+  uint64_t* tmem_full = xf + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xf + 5);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -172,12 +185,16 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (BLO) tma_prefetch_desc(&tmap_blo);
   }
   if (warp_idx == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&xf[s], 128);
+      mbar_init(&lo_empty[s], 1);
     }
     mbar_init(tmem_full, 1);
     fence_barrier_init();
@@ -195,7 +212,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int s = kt % C::STAGES;
         const uint32_t ph = (uint32_t)(kt / C::STAGES) & 1u;
         mbar_wait(&empty[s], ph ^ 1u);
-        mbar_expect_tx(&full[s], TILE_A_BYTES + TILE_B_BYTES);
+        mbar_expect_tx(&full[s], C::STAGE_BYTES);
         const int k_elem = (kt0 + kt) * BK;
         const uint32_t a_dst = smem_u32(tiles + s * C::STAGE_BYTES);
         const uint32_t b_dst = a_dst + TILE_A_BYTES;
@@ -211,6 +228,15 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
           for (int i = 0; i < BN / 32; ++i) tma_load_2d(b_dst + i * 4096, &tmap_b, &full[s], n_blk * BN + i * 32, k_elem);
         }
+        if (BLO) {
+          const uint32_t bl_dst = b_dst + TILE_B_BYTES;
+          if (!B_MN) {
+            tma_load_2d(bl_dst, &tmap_blo, &full[s], k_elem, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 32; ++i) tma_load_2d(bl_dst + i * 4096, &tmap_blo, &full[s], n_blk * BN + i * 32, k_elem);
+          }
+        }
       }
     }
   } else if (warp_idx == 1) {
@@ -222,12 +248,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       for (int kt = 0; kt < num_kt; ++kt) {
         const int s = kt % C::STAGES;
         const uint32_t ph = (uint32_t)(kt / C::STAGES) & 1u;
-        mbar_wait(SPLIT3 ? &xf[s] : &full[s], ph);
+        const int ls = SPLIT3 ? (kt % 2) : 0;
+        mbar_wait(&full[s], ph);
+        if (SPLIT3) mbar_wait(&xf[ls], (uint32_t)(kt / 2) & 1u);
         tc_fence_after();
         const uint32_t a_hi = smem_u32(tiles + s * C::STAGE_BYTES);
         const uint32_t b_hi = a_hi + TILE_A_BYTES;
-        const uint32_t a_lo = b_hi + TILE_B_BYTES;
-        const uint32_t b_lo = a_lo + TILE_A_BYTES;
+        const uint32_t a_lo = smem_u32(lo_tiles + ls * C::LO_STAGE_BYTES);
+        const uint32_t b_lo = BLO ? (b_hi + TILE_B_BYTES) : (a_lo + TILE_A_BYTES);
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
           const uint64_t da = make_smem_desc<A_MN>(a_hi + k * a_kstep);
@@ -242,7 +270,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             umma_tf32(tmem_base, da, db, idesc, (kt > 0 || k > 0) ? 1u : 0u);
           }
         }
-        umma_commit(&empty[s]);     // frees the smem slot when these MMAs retire
+        umma_commit(&empty[s]);     // frees the operand stage when these MMAs retire
+        if (SPLIT3) umma_commit(&lo_empty[ls]);
       }
       umma_commit(tmem_full);       // accumulator complete
     }
@@ -254,17 +283,24 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       for (int kt = 0; kt < num_kt; ++kt) {
         const int s = kt % C::STAGES;
         const uint32_t ph = (uint32_t)(kt / C::STAGES) & 1u;
+        const int ls = kt % 2;
+        mbar_wait(&lo_empty[ls], ((uint32_t)(kt / 2) & 1u) ^ 1u);     // MMAs of k-tile kt-2 no longer read this lo stage
         mbar_wait(&full[s], ph);
         const float4* hi = reinterpret_cast<const float4*>(tiles + s * C::STAGE_BYTES);
-        float4* lo = reinterpret_cast<float4*>(tiles + s * C::STAGE_BYTES + TILE_A_BYTES + TILE_B_BYTES);
-#pragma unroll 4
-        for (int i = te; i < (TILE_A_BYTES + TILE_B_BYTES) / 16; i += 128) {
-          float4 v = hi[i];
-          v.x = tf32_lo(v.x); v.y = tf32_lo(v.y); v.z = tf32_lo(v.z); v.w = tf32_lo(v.w);
-          lo[i] = v;
+        float4* lo = reinterpret_cast<float4*>(lo_tiles + ls * C::LO_STAGE_BYTES);
+        // A (and, without a B_lo plane in HBM, B: the two tiles are contiguous) -> lo.  All loads are issued
+        // before the first use so the split costs one shared-memory round trip per k-tile.
+        constexpr int NV = SPLIT3 ? C::LO_STAGE_BYTES / 16 / 128 : 1;   // float4 per thread: 8 (A only) or 16 (A and B)
+        float4 v[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = hi[te + i * 128];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          v[i].x = tf32_lo(v[i].x); v[i].y = tf32_lo(v[i].y); v[i].z = tf32_lo(v[i].z); v[i].w = tf32_lo(v[i].w);
+          lo[te + i * 128] = v[i];
         }
         fence_proxy_async_smem();
-        mbar_arrive(&xf[s]);
+        mbar_arrive(&xf[ls]);
       }
     }
     // ===== epilogue =====
@@ -342,15 +378,15 @@ static int make_operand_map(const nar_ctx* ctx, CUtensorMap* map, const float* p
   return r == CUDA_SUCCESS ? NAR_OK : NAR_ERR_INVALID;
 }
 
-template <bool A_MN, bool B_MN, bool SPLIT3>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, dim3 grid, cudaStream_t st) {
-  auto kern = gemm_tf32_kernel<A_MN, B_MN, SPLIT3>;
+template <bool A_MN, bool B_MN, bool SPLIT3, bool BLO>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbl, const Params& p, dim3 grid, cudaStream_t st) {
+  auto kern = gemm_tf32_kernel<A_MN, B_MN, SPLIT3, BLO>;
   static bool attr_set = false;     // per instantiation
   if (!attr_set) {
-    NAR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<SPLIT3>::SMEM_BYTES));
+    NAR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<SPLIT3, BLO>::SMEM_BYTES));
     attr_set = true;
   }
-  kern<<<grid, NUM_THREADS, Cfg<SPLIT3>::SMEM_BYTES, st>>>(ta, tb, p);
+  kern<<<grid, NUM_THREADS, Cfg<SPLIT3, BLO>::SMEM_BYTES, st>>>(ta, tb, tbl, p);
   NAR_LAUNCH_CHECK();
   return NAR_OK;
 }
@@ -380,6 +416,12 @@ extern "C" int nar_gemm_tf32(nar_ctx* ctx, int64_t M, int64_t N, int64_t K, cons
   if (rc) return rc;
   rc = make_operand_map(ctx, &tb, B, N, K, ldb, b_kmajor != 0);
   if (rc) return rc;
+  const bool blo = epi->precision == 3 && epi->b_lo != nullptr;
+  CUtensorMap tbl = tb;
+  if (blo) {
+    rc = make_operand_map(ctx, &tbl, epi->b_lo, N, K, ldb, b_kmajor != 0);
+    if (rc) return rc;
+  }
   Params p;
   p.M = M; p.N = N; p.K = K; p.D = D; p.ldd = ldd; p.bias = epi->bias; p.aux = epi->aux; p.ld_aux = epi->ld_aux;
   p.act = epi->act; p.dact = epi->dact; p.accumulate = epi->accumulate; p.k_tiles_per_split = per;
@@ -389,11 +431,11 @@ extern "C" int nar_gemm_tf32(nar_ctx* ctx, int64_t M, int64_t N, int64_t K, cons
   dim3 grid((unsigned)(n_tiles * m_tiles), (unsigned)split, 1);
   cudaStream_t st = as_stream(stream);
   const bool amn = !a_kmajor, bmn = !b_kmajor, s3 = epi->precision == 3;
-#define NAR_GEMM_CASE(a, b, s) if (amn == a && bmn == b && s3 == s) return launch<a, b, s>(ta, tb, p, grid, st);
-  NAR_GEMM_CASE(false, false, false) NAR_GEMM_CASE(false, false, true)
-  NAR_GEMM_CASE(false, true, false)  NAR_GEMM_CASE(false, true, true)
-  NAR_GEMM_CASE(true, false, false)  NAR_GEMM_CASE(true, false, true)
-  NAR_GEMM_CASE(true, true, false)   NAR_GEMM_CASE(true, true, true)
+#define NAR_GEMM_CASE(a, b, s, l) if (amn == a && bmn == b && s3 == s && blo == l) return launch<a, b, s, l>(ta, tb, tbl, p, grid, st);
+  NAR_GEMM_CASE(false, false, false, false) NAR_GEMM_CASE(false, false, true, false) NAR_GEMM_CASE(false, false, true, true)
+  NAR_GEMM_CASE(false, true, false, false)  NAR_GEMM_CASE(false, true, true, false)  NAR_GEMM_CASE(false, true, true, true)
+  NAR_GEMM_CASE(true, false, false, false)  NAR_GEMM_CASE(true, false, true, false)  NAR_GEMM_CASE(true, false, true, true)
+  NAR_GEMM_CASE(true, true, false, false)   NAR_GEMM_CASE(true, true, true, false)   NAR_GEMM_CASE(true, true, true, true)
 #undef NAR_GEMM_CASE
   return NAR_ERR_INVALID;
 }

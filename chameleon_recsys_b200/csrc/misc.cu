@@ -5,12 +5,14 @@
 namespace nar {
 namespace misc {
 
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
 // tf.train.AdamOptimizer (nar_model.py:708-722): lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed on the host
 // in double; w -= lr_t * m / (sqrt(v) + eps).  Elements [0, reg_end) carry an l2_regularizer:
 // their gradient gets + reg_l2 * w (d/dw of reg_l2 * sum(w^2)/2).
 __global__ void __launch_bounds__(256)
 adam_tf_kernel(float4* __restrict__ w, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
-               int64_t n4, int64_t reg_end4, float reg_l2, float lr_t, float b1, float b2, float eps) {
+               int64_t n4, int64_t reg_end4, float reg_l2, float lr_t, float b1, float b2, float eps, float4* __restrict__ wlo) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 wi = w[i], gi = g[i], mi = m[i], vi = v[i];
     const float r = i < reg_end4 ? reg_l2 : 0.f;
@@ -22,7 +24,13 @@ adam_tf_kernel(float4* __restrict__ w, const float4* __restrict__ g, float4* __r
     NAR_ADAM1(x) NAR_ADAM1(y) NAR_ADAM1(z) NAR_ADAM1(w)
 #undef NAR_ADAM1
     w[i] = wi; m[i] = mi; v[i] = vi;
+    if (wlo) wlo[i] = make_float4(tf32_lo(wi.x), tf32_lo(wi.y), tf32_lo(wi.z), tf32_lo(wi.w));
   }
+}
+
+__global__ void __launch_bounds__(256)
+tf32_lo_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ lo) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) lo[i] = tf32_lo(x[i]);
 }
 
 // out[c] += sum_r x[r,c] ; CTA = 256 columns x 64-row slab
@@ -126,14 +134,23 @@ extern "C" int nar_ctx_destroy(nar_ctx* ctx) {
 }
 
 // ------------------------------------------------------------------ helpers
+extern "C" int nar_tf32_lo(const float* x, int64_t n, float* lo, void* stream) {
+  if (!x || !lo) return NAR_ERR_INVALID;
+  if (n <= 0) return NAR_OK;
+  nar::misc::tf32_lo_kernel<<<nar::misc::grid_for(n, 1024), 256, 0, as_stream(stream)>>>(x, n, lo);
+  NAR_LAUNCH_CHECK();
+  return NAR_OK;
+}
+
 extern "C" int nar_adam_tf(float* params, const float* grads, float* m, float* v, int64_t n, int64_t reg_end, float reg_l2,
-                           float lr, float beta1, float beta2, float eps, int64_t step, void* stream) {
+                           float lr, float beta1, float beta2, float eps, int64_t step, float* params_lo, void* stream) {
   if (!params || !grads || !m || !v || (n & 3) || (reg_end & 3) || step < 1) return NAR_ERR_INVALID;
   if (n == 0) return NAR_OK;
   const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
   nar::misc::adam_tf_kernel<<<nar::misc::grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(
       reinterpret_cast<float4*>(params), reinterpret_cast<const float4*>(grads), reinterpret_cast<float4*>(m),
-      reinterpret_cast<float4*>(v), n / 4, reg_end / 4, reg_l2, (float)lr_t, beta1, beta2, eps);
+      reinterpret_cast<float4*>(v), n / 4, reg_end / 4, reg_l2, (float)lr_t, beta1, beta2, eps,
+      reinterpret_cast<float4*>(params_lo));
   NAR_LAUNCH_CHECK();
   return NAR_OK;
 }

@@ -81,6 +81,7 @@ class NarEngine:
         self.grads = torch.zeros(n, device=d)
         self.adam_m = torch.zeros(n, device=d)
         self.adam_v = torch.zeros(n, device=d)
+        self.params_lo = torch.zeros(n, device=d)      # w - tf32_trunc(w): B_lo plane of the 3xTF32 forward GEMMs
         self.global_step = 0
         self.WhT = [torch.zeros(2 * self.Hp, self.Hp, device=d) for _ in range(self.layers)]
         self.stats = torch.zeros(24, device=d)
@@ -110,6 +111,7 @@ class NarEngine:
         flat = self.layout.to_internal(logical)
         self.params.copy_(torch.from_numpy(flat))
         self.adam_m.zero_(); self.adam_v.zero_(); self.grads.zero_()
+        ops.tf32_lo(self.params, self.layout.total, self.params_lo)
         self.global_step = 0
 
     def get_params(self) -> Dict[str, np.ndarray]:
@@ -133,6 +135,7 @@ class NarEngine:
         self.adam_m.copy_(torch.from_numpy(self.layout.to_internal(sd['adam_m'])))
         self.adam_v.copy_(torch.from_numpy(self.layout.to_internal(sd['adam_v'])))
         self.global_step = int(sd['global_step'])
+        ops.tf32_lo(self.params, self.layout.total, self.params_lo)
 
     # ------------------------------------------------------------------ buffers
     def _buf(self, name: str, rows: int, cols: int, dtype=torch.float32) -> torch.Tensor:
@@ -259,7 +262,8 @@ class NarEngine:
         K = W.shape[0] if K is None else K
         N = W.shape[1] if N is None else N
         ops.gemm(X, W, Y, M, N, K, a_kmajor=True, b_kmajor=False, bias=self.view(bkey).view(-1) if bkey else None,
-                 act=act, precision=self.fwd_prec)
+                 act=act, precision=self.fwd_prec,
+                 b_lo=self.view(Wkey, self.params_lo) if self.fwd_prec == 3 else None)
 
     def _dgrad(self, dY, Wkey, dX, M, dact=ACT_NONE, aux=None, N_out=None, K_in=None):
         """dX[M, in] = dY[M, out] * W^T  (W stored [in, out]) optionally times act'(aux)."""
@@ -422,7 +426,7 @@ class NarEngine:
             torch.distributed.all_reduce(self.grads, group=self.pg)
         self.global_step += 1
         ops.adam_tf(self.params, self.grads, self.adam_m, self.adam_v, self.layout.total, self.layout.reg_end,
-                    self.reg, self.lr, self.global_step)
+                    self.reg, self.lr, self.global_step, params_lo=self.params_lo)
 
     def train_step(self, features, labels, buffer, pop_norm, keep: bool = False, sync: bool = True) -> dict:
         st = self.stage(features, labels, buffer, pop_norm)

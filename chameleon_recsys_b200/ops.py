@@ -38,7 +38,7 @@ def _chk_f32(*ts):
 
 def gemm(A: torch.Tensor, B: torch.Tensor, D: torch.Tensor, M: int, N: int, K: int, *, a_kmajor=True, b_kmajor=True,
          lda=None, ldb=None, ldd=None, bias=None, act=ACT_NONE, dact=ACT_NONE, aux=None, ld_aux=None,
-         accumulate=False, split_k=1, precision=3):
+         accumulate=False, split_k=1, precision=3, b_lo=None):
     global LAUNCHES
     LAUNCHES += 1
     """D[M,N] = epilogue(sum_k A(m,k) B(n,k)); see nar_gemm_tf32."""
@@ -47,7 +47,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, D: torch.Tensor, M: int, N: int, K: i
     ldb = B.stride(0) if ldb is None else ldb
     ldd = D.stride(0) if ldd is None else ldd
     epi = GemmEpilogue(_p(bias), act, dact, _p(aux), (aux.stride(0) if (aux is not None and ld_aux is None) else (ld_aux or 0)),
-                       1 if accumulate else 0, int(split_k), int(precision))
+                       1 if accumulate else 0, int(split_k), int(precision), _p(b_lo))
     ctx = context()
     check(ctx.lib.nar_gemm_tf32(ctx.handle, M, N, K, _p(A), lda, 1 if a_kmajor else 0, _p(B), ldb, 1 if b_kmajor else 0,
                                 _p(D), ldd, C.byref(epi), _stream()), 'nar_gemm_tf32')
@@ -192,8 +192,14 @@ def transpose(src, rows, cols, ld_src, dst, ld_dst):
     check(_lib.load().nar_transpose_f32(_p(src), rows, cols, ld_src, _p(dst), ld_dst, _stream()), 'nar_transpose_f32')
 
 
-def adam_tf(params, grads, m, v, n, reg_end, reg_l2, lr, step, beta1=0.9, beta2=0.999, eps=1e-8):
+def adam_tf(params, grads, m, v, n, reg_end, reg_l2, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, params_lo=None):
     global LAUNCHES
     LAUNCHES += 1
     check(_lib.load().nar_adam_tf(_p(params), _p(grads), _p(m), _p(v), n, reg_end, reg_l2, lr, beta1, beta2, eps, step,
-                                  _stream()), 'nar_adam_tf')
+                                  _p(params_lo), _stream()), 'nar_adam_tf')
+
+
+def tf32_lo(x, n, lo):
+    global LAUNCHES
+    LAUNCHES += 1
+    check(_lib.load().nar_tf32_lo(_p(x), n, _p(lo), _stream()), 'nar_tf32_lo')

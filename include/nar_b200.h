@@ -147,6 +147,8 @@ typedef struct {
   int32_t accumulate;     /* 1: D += result with atomics (required when split_k > 1) */
   int32_t split_k;        /* >=1 */
   int32_t precision;      /* 1 = TF32, 3 = 3xTF32 (error-compensated, ~fp32 accuracy) */
+  const float* b_lo;      /* precision 3 only, optional: x - tf32_trunc(x) of operand B, same shape / ld as B (see
+                             nar_tf32_lo; the weights' lo plane is maintained by nar_adam_tf).  NULL: split B in-kernel */
 } nar_gemm_epilogue;
 
 int nar_gemm_tf32(nar_ctx* ctx, int64_t M, int64_t N, int64_t K,
@@ -211,7 +213,10 @@ int nar_transpose_f32(const float* src, int64_t rows, int64_t cols, int64_t ld_s
  *      elements [0,reg_end) gets + reg_l2*w (l2_regularizer); grad is scaled by grad_scale
  *      first (1/world after a sum-allreduce is NOT needed: losses are already global means) */
 int nar_adam_tf(float* params, const float* grads, float* m, float* v, int64_t n, int64_t reg_end,
-                float reg_l2, float lr, float beta1, float beta2, float eps, int64_t step, void* stream);
+                float reg_l2, float lr, float beta1, float beta2, float eps, int64_t step,
+                float* params_lo /* optional [n]: receives w - tf32_trunc(w) of the updated weights */, void* stream);
+/* lo[i] = x[i] - tf32_trunc(x[i])  (the second operand plane of the 3xTF32 GEMM)          */
+int nar_tf32_lo(const float* x, int64_t n, float* lo, void* stream);
 
 #ifdef __cplusplus
 }

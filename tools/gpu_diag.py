@@ -16,7 +16,7 @@ sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, 'gpurun_out')
 
 
-def _gemm_case(a_k, b_k, prec, M, N, K, epi='none', split=1):
+def _gemm_case(a_k, b_k, prec, M, N, K, epi='none', split=1, blo=False):
     import torch
     from chameleon_recsys_b200 import ops
     torch.manual_seed(M * 7 + N * 3 + K)
@@ -52,6 +52,10 @@ def _gemm_case(a_k, b_k, prec, M, N, K, epi='none', split=1):
         D += 1.0
         ref = ref + 1.0
         kw = dict(accumulate=True, split_k=split)
+    if blo:
+        Blo = torch.empty_like(B)
+        ops.tf32_lo(B, B.numel(), Blo)
+        kw['b_lo'] = Blo
     ops.gemm(A, B, D, M, N, K, a_kmajor=a_k, b_kmajor=b_k, lda=lda, ldb=ldb, precision=prec, **kw)
     torch.cuda.synchronize()
     got = D[:, :N].double()
@@ -67,10 +71,11 @@ def _fam_gemm_major(a_k, b_k):
     shapes = [(128, 128, 32), (128, 128, 256), (300, 200, 100), (1000, 510, 1024), (257, 64, 480)]
     for prec in (1, 3):
         for (M, N, K) in shapes:
-            r = _gemm_case(a_k, b_k, prec, M, N, K)
-            r.update(a_k=a_k, b_k=b_k, prec=prec, shape=[M, N, K], epi='none')
-            r['ok'] = (not r['nan']) and r['rel'] < (3e-3 if prec == 1 else 2e-5) and r['pad_untouched']
-            res.append(r)
+            for blo in ((False, True) if prec == 3 else (False,)):
+                r = _gemm_case(a_k, b_k, prec, M, N, K, blo=blo)
+                r.update(a_k=a_k, b_k=b_k, prec=prec, shape=[M, N, K], epi='none', blo=blo)
+                r['ok'] = (not r['nan']) and r['rel'] < (3e-3 if prec == 1 else 2e-5) and r['pad_untouched']
+                res.append(r)
     return res
 
 

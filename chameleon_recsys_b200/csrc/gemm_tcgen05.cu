@@ -4,21 +4,27 @@
 //
 // Replaces every tf.layers.Dense of the reference graph (nar_model.py:375-473) and the UGRNN
 // input projection (:1317); forward, dgrad and wgrad all go through this one kernel by
-// choosing operand majors (no transposed copies of weights or activations are ever made):
-//   fwd   Y  = X  * W        A = X  (K-major)   B = W   (MN-major: W is [in,out], out contiguous)
+// choosing operand majors (no transposed copies of activations are ever made):
+//   fwd   Y  = X  * W        A = X  (K-major)   B = W   (MN-major: W is [in,out]) or W^T (K-major)
 //   dgrad dX = dY * W^T      A = dY (K-major)   B = W   (K-major)
 //   wgrad dW = X^T * dY      A = X  (MN-major)  B = dY  (MN-major), split-K + red.add
 //
-// CTA = 256 threads, one 128x128 fp32 accumulator tile in TMEM (128 columns):
-//   warp 0    TMA producer  (cp.async.bulk.tensor.2d, SWIZZLE_128B, 32 fp32 = 128 B per row)
-//   warp 1    MMA issuer    (one thread, tcgen05.mma.cta_group::1.kind::tf32, M=128 N=128 K=8)
+// CTA = 256 threads; T x T accumulator tiles of 128x128 fp32 in TMEM (T = 1: 128 columns, T = 2: all 512):
+//   warp 0    TMA producer  (cp.async.bulk.tensor.2d, 128-byte swizzle, 32 fp32 = 128 B per row)
+//   warp 1    MMA issuer    (one thread, tcgen05.mma.cta_group::1.kind::tf32, M=128 N=128*T K=8)
 //   warp 2    TMEM allocator
-//   warps 4-7 3xTF32 operand split (lo = x - tf32_trunc(x), written next to the TMA tile)
-//             during the main loop, then the epilogue (tcgen05.ld 32x32b -> bias/activation/
-//             activation-derivative -> st.global.v4 or red.global.add).
+//   warps 4-7 3xTF32 operand split during the main loop, then the epilogue (tcgen05.ld 32x32b ->
+//             bias / activation / activation-derivative -> st.global.v4 or red.global.add).
+//
+// Measured on B200 (ncu, profiles/): with 128x128 fp32 tiles the single-pass kernel asks L2 for 64 B per kMAC
+// and sits at the chip's L2->SM throughput (tensor pipe 20 % busy).  T = 2 (256x256 per CTA, 64 KB per k-tile
+// for 4x the MACs) halves that; it is used for the big single-pass (backward) GEMMs.
+//
 // 3xTF32: the tensor core reads fp32 bits as tf32 by dropping the low 13 mantissa bits, so the
-// "hi" operand is the TMA tile itself; D += Ahi*Bhi + Alo*Bhi + Ahi*Blo restores ~fp32 accuracy
+// "hi" operand is the TMA tile itself; D += Alo*Bhi + Ahi*Blo + Ahi*Bhi restores ~fp32 accuracy
 // (the reference is fp32 end to end and logits are divided by temperature 0.1 before exp).
+//   MODE 0: single pass.   MODE 1: 3x, both lo tiles produced in-kernel.
+//   MODE 2: 3x, B_lo (weights) read from HBM by TMA (nar_adam_tf maintains it), only A is split in-kernel.
 #include "common.cuh"
 
 namespace nar {
@@ -26,26 +32,26 @@ namespace gemm {
 
 constexpr int BM = 128;
 constexpr int BN = 128;
-constexpr int BK = 32;            // 32 fp32 = 128 B = one SWIZZLE_128B span
+constexpr int BK = 32;            // 32 fp32 = 128 B = one 128-byte swizzle span
 constexpr int UMMA_K = 8;         // tf32: 32 B of K per instruction
-constexpr int TILE_A_BYTES = BM * BK * 4;
-constexpr int TILE_B_BYTES = BN * BK * 4;
+constexpr int TILE_BYTES_1 = 128 * BK * 4;     // one 128 x 32 fp32 operand tile
 constexpr int NUM_THREADS = 256;
-constexpr int TMEM_COLS = 128;
 
-// Two shared-memory rings.  The operand ring (TMA destination, the "hi" tiles) is deep so that TMA latency
-// (~1-2 us from L2/HBM under load) is hidden; the 3xTF32 "lo" tiles only live from the split to the MMA that
-// consumes them, so their ring is shallow.  (One combined hi+lo ring allowed 3 stages and left the 3xTF32 GEMMs
-// TMA-latency bound: measured 37 us per 128x128x1024 tile vs 13 us of MMA time.)
-// BLO: the lo plane of operand B (the weights) is read from HBM by TMA (nar_adam_tf maintains it), so the in-kernel
-// split only touches the A tile: operand stage = A | B | B_lo (48 KB), lo ring = A_lo only (16 KB).
-template <bool SPLIT3, bool BLO> struct Cfg {
-  static constexpr int STAGE_BYTES = TILE_A_BYTES + TILE_B_BYTES * (BLO ? 2 : 1);   // one operand stage (A | B [| B_lo])
-  static constexpr int LO_STAGE_BYTES = SPLIT3 ? (BLO ? TILE_A_BYTES : TILE_A_BYTES + TILE_B_BYTES) : 0;
-  static constexpr int STAGES = SPLIT3 ? (BLO ? 4 : 5) : 6;                 // operand ring depth
-  static constexpr int LO_STAGES = SPLIT3 ? 2 : 0;                          // lo ring depth
+// Two shared-memory rings.  The operand ring (TMA destination) is deep to hide TMA latency; the 3xTF32 "lo"
+// tiles only live from the split to the MMAs that consume them, so their ring is shallow.
+template <int MODE, int T> struct Cfg {
+  static constexpr bool SPLIT3 = MODE != 0;
+  static constexpr bool BLO = MODE == 2;
+  static constexpr int A_BYTES = T * TILE_BYTES_1;
+  static constexpr int B_BYTES = T * TILE_BYTES_1;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES * (BLO ? 2 : 1);     // one operand stage (A | B [| B_lo])
+  static constexpr int LO_STAGE_BYTES = SPLIT3 ? (BLO ? A_BYTES : A_BYTES + B_BYTES) : 0;
+  static constexpr int STAGES = SPLIT3 ? (BLO ? 4 : 5) : (T == 2 ? 3 : 6);  // operand ring depth
+  static constexpr int LO_STAGES = SPLIT3 ? 2 : 0;
   static constexpr int TILE_BYTES = STAGES * STAGE_BYTES + LO_STAGES * LO_STAGE_BYTES;
   static constexpr int SMEM_BYTES = TILE_BYTES + 256 + 1024;                // tiles + barriers + align slack
+  static constexpr int TMEM_COLS = T * T * 128;                             // 128 or 512
+  static_assert(T == 1 || MODE == 0, "256x256 tiles only in single-pass mode (shared memory)");
 };
 
 struct Params {
@@ -142,25 +148,75 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 
-// instruction descriptor (UMMA::InstrDescriptor): c_format F32 (1<<4), a/b format TF32 (2<<7, 2<<10),
-// a_major bit 15, b_major bit 16 (1 = MN-major), N>>3 at [17,23), M>>4 at [24,29)
-template <bool A_MN, bool B_MN>
-__device__ __forceinline__ constexpr uint32_t make_idesc() {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-}
-
 __device__ __forceinline__ float tf32_lo(float x) {
   return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
 }
 
+
+// instruction descriptor (UMMA::InstrDescriptor): c_format F32 (1<<4), a/b format TF32 (2<<7, 2<<10),
+// a_major bit 15, b_major bit 16 (1 = MN-major), N>>3 at [17,23), M>>4 at [24,29)
+template <bool A_MN, bool B_MN, int N>
+__device__ __forceinline__ constexpr uint32_t make_idesc_n() {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// one 32-column chunk of one accumulator row: bias / activation / activation-derivative / store
+__device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (&r)[32], int64_t row, int64_t col0) {
+  float* drow = p.D + row * p.ldd + col0;
+  const float* arow = p.dact ? (p.aux + row * p.ld_aux + col0) : nullptr;
+  if (col0 + 32 <= p.N) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+      if (p.bias) {
+        const float4 b = *reinterpret_cast<const float4*>(p.bias + col0 + j);
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+      }
+      if (p.act) { v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act); v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act); }
+      if (p.dact) {
+        const float4 a = *reinterpret_cast<const float4*>(arow + j);
+        v.x *= act_grad_from_output(a.x, p.dact); v.y *= act_grad_from_output(a.y, p.dact);
+        v.z *= act_grad_from_output(a.z, p.dact); v.w *= act_grad_from_output(a.w, p.dact);
+      }
+      if (p.accumulate) {
+        atomicAdd(drow + j, v.x); atomicAdd(drow + j + 1, v.y); atomicAdd(drow + j + 2, v.z); atomicAdd(drow + j + 3, v.w);
+      } else {
+        *reinterpret_cast<float4*>(drow + j) = v;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (col0 + j < p.N) {
+        float v = __uint_as_float(r[j]);
+        if (p.bias) v += p.bias[col0 + j];
+        v = apply_act(v, p.act);
+        if (p.dact) v *= act_grad_from_output(arow[j], p.dact);
+        if (p.accumulate) atomicAdd(drow + j, v); else drow[j] = v;
+      }
+    }
+  }
+}
+
+// TMA for one operand tile of `rows_mn` (= 128*T) MN rows at MN coordinate mn0, K element k_elem
+template <bool MN_MAJOR, int T>
+__device__ __forceinline__ void load_operand(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int mn0, int k_elem) {
+  if (!MN_MAJOR) {
+    tma_load_2d(dst, map, bar, k_elem, mn0);                       // one box: 128*T rows x 128 B
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4 * T; ++i) tma_load_2d(dst + i * 4096, map, bar, mn0 + i * 32, k_elem);   // boxes of 32 MN x 32 k
+  }
+}
+
 // ---------------------------------------------------------------- kernel
-template <bool A_MN, bool B_MN, bool SPLIT3, bool BLO>
+template <bool A_MN, bool B_MN, int MODE, int T>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_blo, const Params p) {
-  using C = Cfg<SPLIT3, BLO>;
-  static_assert(!BLO || SPLIT3, "B_lo only exists in 3xTF32 mode");
+  using C = Cfg<MODE, T>;
+  constexpr bool SPLIT3 = C::SPLIT3, BLO = C::BLO;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -169,8 +225,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::TILE_BYTES);
   uint64_t* full = bars;                          // [STAGES]    TMA landed
   uint64_t* empty = bars + C::STAGES;             // [STAGES]    MMAs that read the operand stage retired
-  uint64_t* xf = bars + 2 * C::STAGES;            // [LO_STAGES] lo tiles written (128 arrivals)
-  uint64_t* lo_empty = xf + 2;                    // [LO_STAGES] MMAs that read the lo stage retired
+  uint64_t* xf = bars + 2 * C::STAGES;            // [2] lo tiles written (128 arrivals)
+  uint64_t* lo_empty = xf + 2;                    // [2] MMAs that read the lo stage retired
   uint64_t* tmem_full = xf + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xf + 5);
 
@@ -199,7 +255,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     mbar_init(tmem_full, 1);
     fence_barrier_init();
   }
-  if (warp_idx == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp_idx == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -215,34 +271,16 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         mbar_expect_tx(&full[s], C::STAGE_BYTES);
         const int k_elem = (kt0 + kt) * BK;
         const uint32_t a_dst = smem_u32(tiles + s * C::STAGE_BYTES);
-        const uint32_t b_dst = a_dst + TILE_A_BYTES;
-        if (!A_MN) {
-          tma_load_2d(a_dst, &tmap_a, &full[s], k_elem, m_blk * BM);
-        } else {
-#pragma unroll
-          for (int i = 0; i < BM / 32; ++i) tma_load_2d(a_dst + i * 4096, &tmap_a, &full[s], m_blk * BM + i * 32, k_elem);
-        }
-        if (!B_MN) {
-          tma_load_2d(b_dst, &tmap_b, &full[s], k_elem, n_blk * BN);
-        } else {
-#pragma unroll
-          for (int i = 0; i < BN / 32; ++i) tma_load_2d(b_dst + i * 4096, &tmap_b, &full[s], n_blk * BN + i * 32, k_elem);
-        }
-        if (BLO) {
-          const uint32_t bl_dst = b_dst + TILE_B_BYTES;
-          if (!B_MN) {
-            tma_load_2d(bl_dst, &tmap_blo, &full[s], k_elem, n_blk * BN);
-          } else {
-#pragma unroll
-            for (int i = 0; i < BN / 32; ++i) tma_load_2d(bl_dst + i * 4096, &tmap_blo, &full[s], n_blk * BN + i * 32, k_elem);
-          }
-        }
+        const uint32_t b_dst = a_dst + C::A_BYTES;
+        load_operand<A_MN, T>(a_dst, &tmap_a, &full[s], m_blk * BM * T, k_elem);
+        load_operand<B_MN, T>(b_dst, &tmap_b, &full[s], n_blk * BN * T, k_elem);
+        if (BLO) load_operand<B_MN, T>(b_dst + C::B_BYTES, &tmap_blo, &full[s], n_blk * BN * T, k_elem);
       }
     }
   } else if (warp_idx == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      constexpr uint32_t idesc = make_idesc<A_MN, B_MN>();
+      constexpr uint32_t idesc = make_idesc_n<A_MN, B_MN, BN * T>();
       constexpr uint32_t a_kstep = A_MN ? 1024u : (uint32_t)(UMMA_K * 4);
       constexpr uint32_t b_kstep = B_MN ? 1024u : (uint32_t)(UMMA_K * 4);
       for (int kt = 0; kt < num_kt; ++kt) {
@@ -253,32 +291,38 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (SPLIT3) mbar_wait(&xf[ls], (uint32_t)(kt / 2) & 1u);
         tc_fence_after();
         const uint32_t a_hi = smem_u32(tiles + s * C::STAGE_BYTES);
-        const uint32_t b_hi = a_hi + TILE_A_BYTES;
+        const uint32_t b_hi = a_hi + C::A_BYTES;
         const uint32_t a_lo = smem_u32(lo_tiles + ls * C::LO_STAGE_BYTES);
-        const uint32_t b_lo = BLO ? (b_hi + TILE_B_BYTES) : (a_lo + TILE_A_BYTES);
+        const uint32_t b_lo = BLO ? (b_hi + C::B_BYTES) : (a_lo + C::A_BYTES);
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t da = make_smem_desc<A_MN>(a_hi + k * a_kstep);
           const uint64_t db = make_smem_desc<B_MN>(b_hi + k * b_kstep);
-          if (SPLIT3) {
-            const uint64_t dal = make_smem_desc<A_MN>(a_lo + k * a_kstep);
-            const uint64_t dbl = make_smem_desc<B_MN>(b_lo + k * b_kstep);
-            umma_tf32(tmem_base, dal, db, idesc, (kt > 0 || k > 0) ? 1u : 0u);   // small terms first
-            umma_tf32(tmem_base, da, dbl, idesc, 1u);
-            umma_tf32(tmem_base, da, db, idesc, 1u);
-          } else {
-            umma_tf32(tmem_base, da, db, idesc, (kt > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+          for (int tm = 0; tm < T; ++tm) {
+            const uint32_t acc = tmem_base + (uint32_t)(tm * BN * T);          // accumulator tm: columns [tm*128*T, ...)
+            const uint32_t a_tm = a_hi + tm * TILE_BYTES_1 + k * a_kstep;       // MN-major: 4 boxes of 4096 B = TILE_BYTES_1
+            const uint64_t da = make_smem_desc<A_MN>(a_tm);
+            const uint32_t first = (kt > 0 || k > 0) ? 1u : 0u;
+            if (SPLIT3) {
+              const uint64_t dal = make_smem_desc<A_MN>(a_lo + tm * TILE_BYTES_1 + k * a_kstep);
+              const uint64_t dbl = make_smem_desc<B_MN>(b_lo + k * b_kstep);
+              umma_tf32(acc, dal, db, idesc, first);     // small terms first
+              umma_tf32(acc, da, dbl, idesc, 1u);
+              umma_tf32(acc, da, db, idesc, 1u);
+            } else {
+              umma_tf32(acc, da, db, idesc, first);
+            }
           }
         }
         umma_commit(&empty[s]);     // frees the operand stage when these MMAs retire
         if (SPLIT3) umma_commit(&lo_empty[ls]);
       }
-      umma_commit(tmem_full);       // accumulator complete
+      umma_commit(tmem_full);       // accumulators complete
     }
   } else if (warp_idx >= 4) {
     const int ew = warp_idx - 4;            // TMEM lane quadrant == warp_idx % 4
     if (SPLIT3) {
-      // ===== operand split: lo = x - trunc_tf32(x) for the A and B tiles of each stage =====
+      // ===== operand split: lo = x - trunc_tf32(x) =====
       const int te = threadIdx.x - 128;
       for (int kt = 0; kt < num_kt; ++kt) {
         const int s = kt % C::STAGES;
@@ -306,47 +350,16 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ===== epilogue =====
     mbar_wait(tmem_full, 0);
     tc_fence_after();
-    const int64_t row = (int64_t)m_blk * BM + ew * 32 + lane;
-    const bool row_ok = row < p.M;
-    for (int c = 0; c < BN; c += 32) {
-      const int64_t col0 = (int64_t)n_blk * BN + c;
-      if (col0 >= p.N) break;               // warp-uniform
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c, r);
-      if (!row_ok) continue;
-      float* drow = p.D + row * p.ldd + col0;
-      const float* arow = p.dact ? (p.aux + row * p.ld_aux + col0) : nullptr;
-      if (col0 + 32 <= p.N) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-          if (p.bias) {
-            const float4 b = *reinterpret_cast<const float4*>(p.bias + col0 + j);
-            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-          }
-          if (p.act) { v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act); v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act); }
-          if (p.dact) {
-            const float4 a = *reinterpret_cast<const float4*>(arow + j);
-            v.x *= act_grad_from_output(a.x, p.dact); v.y *= act_grad_from_output(a.y, p.dact);
-            v.z *= act_grad_from_output(a.z, p.dact); v.w *= act_grad_from_output(a.w, p.dact);
-          }
-          if (p.accumulate) {
-            atomicAdd(drow + j, v.x); atomicAdd(drow + j + 1, v.y); atomicAdd(drow + j + 2, v.z); atomicAdd(drow + j + 3, v.w);
-          } else {
-            *reinterpret_cast<float4*>(drow + j) = v;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (col0 + j < p.N) {
-            float v = __uint_as_float(r[j]);
-            if (p.bias) v += p.bias[col0 + j];
-            v = apply_act(v, p.act);
-            if (p.dact) v *= act_grad_from_output(arow[j], p.dact);
-            if (p.accumulate) atomicAdd(drow + j, v); else drow[j] = v;
-          }
-        }
+    for (int tm = 0; tm < T; ++tm) {
+      const int64_t row = ((int64_t)m_blk * T + tm) * BM + ew * 32 + lane;
+      const bool row_ok = row < p.M;
+      for (int c = 0; c < BN * T; c += 32) {
+        const int64_t col0 = (int64_t)n_blk * BN * T + c;
+        if (col0 >= p.N) break;               // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(tm * BN * T + c), r);
+        if (row_ok) epilogue_chunk(p, r, row, col0);
       }
     }
   }
@@ -354,7 +367,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   __syncthreads();
   if (warp_idx == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -363,11 +376,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// operand with logical shape [mn, k]; kmajor: ptr[mn*ld + k] else ptr[k*ld + mn]
-static int make_operand_map(const nar_ctx* ctx, CUtensorMap* map, const float* ptr, int64_t mn, int64_t k, int64_t ld, bool kmajor) {
+// operand with logical shape [mn, k]; kmajor: ptr[mn*ld + k] else ptr[k*ld + mn]; T = tile multiplier
+static int make_operand_map(const nar_ctx* ctx, CUtensorMap* map, const float* ptr, int64_t mn, int64_t k, int64_t ld, bool kmajor, int T) {
   if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0 || (ld & 3) != 0 || ld <= 0) return NAR_ERR_INVALID;
   cuuint64_t dims[2]; cuuint64_t strides[1]; cuuint32_t box[2]; cuuint32_t estr[2] = {1, 1};
-  if (kmajor) { dims[0] = (cuuint64_t)k; dims[1] = (cuuint64_t)mn; box[0] = BK; box[1] = BM; }
+  if (kmajor) { dims[0] = (cuuint64_t)k; dims[1] = (cuuint64_t)mn; box[0] = BK; box[1] = (cuuint32_t)(128 * T); }
   else        { dims[0] = (cuuint64_t)mn; dims[1] = (cuuint64_t)k; box[0] = 32; box[1] = BK; }
   strides[0] = (cuuint64_t)ld * 4;
   CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
@@ -378,15 +391,15 @@ static int make_operand_map(const nar_ctx* ctx, CUtensorMap* map, const float* p
   return r == CUDA_SUCCESS ? NAR_OK : NAR_ERR_INVALID;
 }
 
-template <bool A_MN, bool B_MN, bool SPLIT3, bool BLO>
+template <bool A_MN, bool B_MN, int MODE, int T>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbl, const Params& p, dim3 grid, cudaStream_t st) {
-  auto kern = gemm_tf32_kernel<A_MN, B_MN, SPLIT3, BLO>;
+  auto kern = gemm_tf32_kernel<A_MN, B_MN, MODE, T>;
   static bool attr_set = false;     // per instantiation
   if (!attr_set) {
-    NAR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<SPLIT3, BLO>::SMEM_BYTES));
+    NAR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE, T>::SMEM_BYTES));
     attr_set = true;
   }
-  kern<<<grid, NUM_THREADS, Cfg<SPLIT3, BLO>::SMEM_BYTES, st>>>(ta, tb, tbl, p);
+  kern<<<grid, NUM_THREADS, Cfg<MODE, T>::SMEM_BYTES, st>>>(ta, tb, tbl, p);
   NAR_LAUNCH_CHECK();
   return NAR_OK;
 }
@@ -405,37 +418,52 @@ extern "C" int nar_gemm_tf32(nar_ctx* ctx, int64_t M, int64_t N, int64_t K, cons
   if (epi->bias && (reinterpret_cast<uintptr_t>(epi->bias) & 15u) != 0) return NAR_ERR_INVALID;
   if (epi->dact && (!epi->aux || (epi->ld_aux & 3) != 0 || (reinterpret_cast<uintptr_t>(epi->aux) & 15u) != 0)) return NAR_ERR_INVALID;
   if (epi->precision != 1 && epi->precision != 3) return NAR_ERR_INVALID;
+  const bool blo = epi->precision == 3 && epi->b_lo != nullptr;
+  const int mode = epi->precision == 1 ? 0 : (blo ? 2 : 1);
+  // 256x256 CTA tiles for the big single-pass GEMMs (L2-bound with 128x128 tiles); 128x128 otherwise
+  const int T = (mode == 0 && M >= 256 && N >= 256 && (double)M * (double)N * (double)K >= 4e9) ? 2 : 1;
+  const int64_t n_tiles = (N + BN * T - 1) / (BN * T), m_tiles = (M + BM * T - 1) / (BM * T);
+  if (n_tiles * m_tiles > 0x7fffffffLL) return NAR_ERR_UNSUPPORTED;
   const int k_tiles = (int)((K + BK - 1) / BK);
-  int split = epi->split_k < 1 ? 1 : epi->split_k;
+  int split = epi->split_k;
+  if (split <= 0) {          // auto: about two waves of CTAs, at least 8 k-tiles per split
+    split = 1;
+    if (epi->accumulate) {
+      const int64_t want = (2 * (int64_t)ctx->sm_count + n_tiles * m_tiles - 1) / (n_tiles * m_tiles);
+      const int64_t cap = k_tiles / 8 > 1 ? k_tiles / 8 : 1;
+      split = (int)(want < cap ? want : cap);
+      if (split < 1) split = 1;
+    }
+  }
   if (split > k_tiles) split = k_tiles;
   if (split > 1 && !epi->accumulate) return NAR_ERR_INVALID;
   int per = (k_tiles + split - 1) / split;
   split = (k_tiles + per - 1) / per;          // no empty splits
   CUtensorMap ta, tb;
-  int rc = make_operand_map(ctx, &ta, A, M, K, lda, a_kmajor != 0);
+  int rc = make_operand_map(ctx, &ta, A, M, K, lda, a_kmajor != 0, T);
   if (rc) return rc;
-  rc = make_operand_map(ctx, &tb, B, N, K, ldb, b_kmajor != 0);
+  rc = make_operand_map(ctx, &tb, B, N, K, ldb, b_kmajor != 0, T);
   if (rc) return rc;
-  const bool blo = epi->precision == 3 && epi->b_lo != nullptr;
   CUtensorMap tbl = tb;
   if (blo) {
-    rc = make_operand_map(ctx, &tbl, epi->b_lo, N, K, ldb, b_kmajor != 0);
+    rc = make_operand_map(ctx, &tbl, epi->b_lo, N, K, ldb, b_kmajor != 0, T);
     if (rc) return rc;
   }
   Params p;
   p.M = M; p.N = N; p.K = K; p.D = D; p.ldd = ldd; p.bias = epi->bias; p.aux = epi->aux; p.ld_aux = epi->ld_aux;
   p.act = epi->act; p.dact = epi->dact; p.accumulate = epi->accumulate; p.k_tiles_per_split = per;
-  const int64_t n_tiles = (N + BN - 1) / BN, m_tiles = (M + BM - 1) / BM;
-  if (n_tiles * m_tiles > 0x7fffffffLL) return NAR_ERR_UNSUPPORTED;
   p.n_tiles = (int)n_tiles;
   dim3 grid((unsigned)(n_tiles * m_tiles), (unsigned)split, 1);
   cudaStream_t st = as_stream(stream);
-  const bool amn = !a_kmajor, bmn = !b_kmajor, s3 = epi->precision == 3;
-#define NAR_GEMM_CASE(a, b, s, l) if (amn == a && bmn == b && s3 == s && blo == l) return launch<a, b, s, l>(ta, tb, tbl, p, grid, st);
-  NAR_GEMM_CASE(false, false, false, false) NAR_GEMM_CASE(false, false, true, false) NAR_GEMM_CASE(false, false, true, true)
-  NAR_GEMM_CASE(false, true, false, false)  NAR_GEMM_CASE(false, true, true, false)  NAR_GEMM_CASE(false, true, true, true)
-  NAR_GEMM_CASE(true, false, false, false)  NAR_GEMM_CASE(true, false, true, false)  NAR_GEMM_CASE(true, false, true, true)
-  NAR_GEMM_CASE(true, true, false, false)   NAR_GEMM_CASE(true, true, true, false)   NAR_GEMM_CASE(true, true, true, true)
+  const bool amn = !a_kmajor, bmn = !b_kmajor;
+#define NAR_GEMM_CASE(a, b) \
+  if (amn == a && bmn == b) { \
+    if (mode == 0 && T == 1) return launch<a, b, 0, 1>(ta, tb, tbl, p, grid, st); \
+    if (mode == 0 && T == 2) return launch<a, b, 0, 2>(ta, tb, tbl, p, grid, st); \
+    if (mode == 1) return launch<a, b, 1, 1>(ta, tb, tbl, p, grid, st); \
+    if (mode == 2) return launch<a, b, 2, 1>(ta, tb, tbl, p, grid, st); \
+  }
+  NAR_GEMM_CASE(false, false) NAR_GEMM_CASE(false, true) NAR_GEMM_CASE(true, false) NAR_GEMM_CASE(true, true)
 #undef NAR_GEMM_CASE
   return NAR_ERR_INVALID;
 }

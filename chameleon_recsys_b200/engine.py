@@ -284,7 +284,7 @@ class NarEngine:
         n_in = dW.shape[0] if n_in is None else n_in
         n_out = dW.shape[1] if n_out is None else n_out
         ops.gemm(X, dY, dW, n_in, n_out, rows, a_kmajor=False, b_kmajor=False, accumulate=True,
-                 split_k=self._split(n_in, n_out, rows), precision=self.bwd_prec)
+                 split_k=0, precision=self.bwd_prec)      # 0 = library picks the split (about two waves of CTAs)
 
     def _bgrad(self, dY, bkey, rows, cols):
         ops.colsum_add(dY, rows, cols, dY.stride(0), self.view(bkey, self.grads).view(-1))

@@ -91,10 +91,21 @@ def fam_gemm_epi():
         r = _gemm_case(True, True, 3, 333, 250, 200, epi)
         r.update(epi=epi, ok=(not r['nan']) and r['rel'] < 5e-5 and r['pad_untouched'])
         res.append(r)
-    for split in (1, 4, 13):
+    for split in (1, 4, 13, 0):
         r = _gemm_case(True, True, 1, 480, 1024, 5000, 'accum', split)
         r.update(epi='accum', split=split, ok=(not r['nan']) and r['rel'] < 3e-3)
         res.append(r)
+    # 256x256 CTA tiles (chosen by the library for big single-pass problems), all operand majors, ragged edges
+    for (a_k, b_k) in ((True, True), (True, False), (False, True), (False, False)):
+        r = _gemm_case(a_k, b_k, 1, 3000, 1000, 2040)
+        r.update(a_k=a_k, b_k=b_k, shape=[3000, 1000, 2040], epi='T2', ok=(not r['nan']) and r['rel'] < 3e-3 and r['pad_untouched'])
+        res.append(r)
+    r = _gemm_case(False, False, 1, 1024, 1000, 20000, 'accum', 0)
+    r.update(epi='T2 accum auto-split', ok=(not r['nan']) and r['rel'] < 3e-3)
+    res.append(r)
+    r = _gemm_case(True, True, 1, 3000, 1024, 2048, 'dact_tanh')
+    r.update(epi='T2 dact', ok=(not r['nan']) and r['rel'] < 3e-3)
+    res.append(r)
     return res
 
 

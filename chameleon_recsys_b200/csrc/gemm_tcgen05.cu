@@ -161,43 +161,39 @@ __device__ __forceinline__ constexpr uint32_t make_idesc_n() {
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-// one 32-column chunk of one accumulator row: bias / activation / activation-derivative / store
-__device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (&r)[32], int64_t row, int64_t col0) {
-  float* drow = p.D + row * p.ldd + col0;
-  const float* arow = p.dact ? (p.aux + row * p.ld_aux + col0) : nullptr;
-  if (col0 + 32 <= p.N) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-      if (p.bias) {
-        const float4 b = *reinterpret_cast<const float4*>(p.bias + col0 + j);
-        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-      }
-      if (p.act) { v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act); v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act); }
-      if (p.dact) {
-        const float4 a = *reinterpret_cast<const float4*>(arow + j);
-        v.x *= act_grad_from_output(a.x, p.dact); v.y *= act_grad_from_output(a.y, p.dact);
-        v.z *= act_grad_from_output(a.z, p.dact); v.w *= act_grad_from_output(a.w, p.dact);
-      }
-      if (p.accumulate) {
-        atomicAdd(drow + j, v.x); atomicAdd(drow + j + 1, v.y); atomicAdd(drow + j + 2, v.z); atomicAdd(drow + j + 3, v.w);
-      } else {
-        *reinterpret_cast<float4*>(drow + j) = v;
-      }
+// Epilogue element work for 4 consecutive columns of one row: bias / activation / activation-derivative / store.
+// Called after the shared-memory transpose, so the 8 lanes that share a row touch 128 contiguous bytes of D / aux.
+__device__ __forceinline__ void epilogue_store4(const Params& p, float4 v, int64_t row, int64_t col) {
+  float* d = p.D + row * p.ldd + col;
+  if (col + 4 <= p.N) {
+    if (p.bias) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
     }
+    if (p.act) { v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act); v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act); }
+    if (p.dact) {
+      const float4 a = *reinterpret_cast<const float4*>(p.aux + row * p.ld_aux + col);
+      v.x *= act_grad_from_output(a.x, p.dact); v.y *= act_grad_from_output(a.y, p.dact);
+      v.z *= act_grad_from_output(a.z, p.dact); v.w *= act_grad_from_output(a.w, p.dact);
+    }
+    if (p.accumulate) atomicAdd(reinterpret_cast<float4*>(d), v);        // red.global.add.v4.f32
+    else *reinterpret_cast<float4*>(d) = v;
   } else {
+    const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (col0 + j < p.N) {
-        float v = __uint_as_float(r[j]);
-        if (p.bias) v += p.bias[col0 + j];
-        v = apply_act(v, p.act);
-        if (p.dact) v *= act_grad_from_output(arow[j], p.dact);
-        if (p.accumulate) atomicAdd(drow + j, v); else drow[j] = v;
+    for (int j = 0; j < 4; ++j) {
+      if (col + j < p.N) {
+        float x = e[j];
+        if (p.bias) x += p.bias[col + j];
+        x = apply_act(x, p.act);
+        if (p.dact) x *= act_grad_from_output(p.aux[row * p.ld_aux + col + j], p.dact);
+        if (p.accumulate) atomicAdd(d + j, x); else d[j] = x;
       }
     }
   }
 }
+
+constexpr int STAGE_LD = 36;      // floats per staged accumulator row (32 + 4: 16-byte aligned, conflict-free)
 
 // TMA for one operand tile of `rows_mn` (= 128*T) MN rows at MN coordinate mn0, K element k_elem
 template <bool MN_MAJOR, int T>
@@ -348,18 +344,33 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
     // ===== epilogue =====
+    // tcgen05.ld 32x32b hands thread i row i of the warp's 32-row slab; a direct store would touch 32 different
+    // 128-byte lines per instruction.  Each 32x32 chunk is transposed through shared memory (the operand ring is
+    // idle by now) so that 8 lanes cover one row's 128 contiguous bytes: coalesced D stores and aux loads.
     mbar_wait(tmem_full, 0);
     tc_fence_after();
+    float* stage = reinterpret_cast<float*>(tiles) + ew * (32 * STAGE_LD);
+    const int rsub = lane >> 3, c4 = (lane & 7) * 4;
 #pragma unroll
     for (int tm = 0; tm < T; ++tm) {
-      const int64_t row = ((int64_t)m_blk * T + tm) * BM + ew * 32 + lane;
-      const bool row_ok = row < p.M;
+      const int64_t row_base = ((int64_t)m_blk * T + tm) * BM + ew * 32;
       for (int c = 0; c < BN * T; c += 32) {
         const int64_t col0 = (int64_t)n_blk * BN * T + c;
         if (col0 >= p.N) break;               // warp-uniform
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(tm * BN * T + c), r);
-        if (row_ok) epilogue_chunk(p, r, row, col0);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(stage + lane * STAGE_LD + j) =
+              make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rl = it * 4 + rsub;
+          const float4 v = *reinterpret_cast<const float4*>(stage + rl * STAGE_LD + c4);
+          if (row_base + rl < p.M) epilogue_store4(p, v, row_base + rl, col0 + c4);
+        }
+        __syncwarp();
       }
     }
   }

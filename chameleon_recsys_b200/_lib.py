@@ -66,7 +66,7 @@ _SIGNATURES = {
     'nar_sample_negatives_workspace': (C.c_int, [i64, i64, i64, i64, C.POINTER(i64)]),
     'nar_sample_negatives': (C.c_int, [vp, vp, i64, i64, i64, i64, vp, i64, i64, i64, u64, u32, vp, vp, i64, vp]),
     'nar_mul_pred': (C.c_int, [vp, vp, i64, i64, i64, vp, vp]),
-    'nar_mul_pred_bwd': (C.c_int, [vp, vp, vp, i64, i64, i64, vp, vp, vp]),
+    'nar_mul_pred_bwd': (C.c_int, [vp, vp, vp, i64, i64, i64, C.c_int, vp, vp, vp]),
     'nar_score_softmax_ce': (C.c_int, [vp, i64, i64, vp, i64, vp, i64, i64, f32, f32, vp, vp, vp, vp, vp, vp]),
     'nar_cosine_softmax_ce': (C.c_int, [vp, vp, i64, i64, i64, f32, f32, vp, vp, vp, vp, vp]),
     'nar_colsum_add': (C.c_int, [vp, i64, i64, i64, vp, vp]),

@@ -163,7 +163,7 @@ __device__ __forceinline__ constexpr uint32_t make_idesc_n() {
 
 // Epilogue element work for 4 consecutive columns of one row: bias / activation / activation-derivative / store.
 // Called after the shared-memory transpose, so the 8 lanes that share a row touch 128 contiguous bytes of D / aux.
-__device__ __forceinline__ void epilogue_store4(const Params& p, float4 v, int64_t row, int64_t col) {
+__device__ __forceinline__ void epilogue_store4(const Params& p, float4 v, int64_t row, int64_t col, const float4& a) {
   float* d = p.D + row * p.ldd + col;
   if (col + 4 <= p.N) {
     if (p.bias) {
@@ -171,8 +171,7 @@ __device__ __forceinline__ void epilogue_store4(const Params& p, float4 v, int64
       v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
     }
     if (p.act) { v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act); v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act); }
-    if (p.dact) {
-      const float4 a = *reinterpret_cast<const float4*>(p.aux + row * p.ld_aux + col);
+    if (p.dact) {        // `a` = aux[row, col..col+3], prefetched by the caller for the whole chunk
       v.x *= act_grad_from_output(a.x, p.dact); v.y *= act_grad_from_output(a.y, p.dact);
       v.z *= act_grad_from_output(a.z, p.dact); v.w *= act_grad_from_output(a.w, p.dact);
     }
@@ -364,11 +363,23 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           *reinterpret_cast<float4*>(stage + lane * STAGE_LD + j) =
               make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
         __syncwarp();
+        // aux (forward output of the layer being differentiated) for the whole chunk first: 8 independent 128-bit
+        // loads in flight instead of a load -> use -> store chain per row (D may alias aux, so the compiler cannot
+        // hoist them itself; every element is read before it is overwritten, rows of different iterations differ)
+        float4 av[8];
+        if (p.dact) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int64_t row = row_base + it * 4 + rsub;
+            av[it] = (row < p.M && col0 + c4 + 4 <= p.N)
+                         ? *reinterpret_cast<const float4*>(p.aux + row * p.ld_aux + col0 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int rl = it * 4 + rsub;
           const float4 v = *reinterpret_cast<const float4*>(stage + rl * STAGE_LD + c4);
-          if (row_base + rl < p.M) epilogue_store4(p, v, row_base + rl, col0 + c4);
+          if (row_base + rl < p.M) epilogue_store4(p, v, row_base + rl, col0 + c4, av[it]);
         }
         __syncwarp();
       }

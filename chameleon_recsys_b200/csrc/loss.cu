@@ -23,7 +23,7 @@ mul_pred_kernel(const float4* __restrict__ cand, const float4* __restrict__ pred
 // one CTA per position: d_cand rows written, d_pred reduced over the n_cand candidates (no atomics)
 __global__ void __launch_bounds__(256)
 mul_pred_bwd_kernel(const float4* __restrict__ d_prod, const float4* __restrict__ cand, const float4* __restrict__ pred,
-                    int64_t n_cand, int C4, float4* __restrict__ d_cand, float4* __restrict__ d_pred) {
+                    int64_t n_cand, int C4, int cand_act, float4* __restrict__ d_cand, float4* __restrict__ d_pred) {
   const int64_t l = blockIdx.x;
   for (int c = threadIdx.x; c < C4; c += blockDim.x) {
     const float4 p = pred[l * C4 + c];
@@ -31,7 +31,9 @@ mul_pred_bwd_kernel(const float4* __restrict__ d_prod, const float4* __restrict_
     for (int64_t j = 0; j < n_cand; ++j) {
       const int64_t i = (l * n_cand + j) * C4 + c;
       const float4 d = d_prod[i]; const float4 e = cand[i];
-      d_cand[i] = make_float4(d.x * p.x, d.y * p.y, d.z * p.z, d.w * p.w);
+      // optionally straight through the activation that produced cand (CAR tanh): d_cand is then d(pre-activation)
+      d_cand[i] = make_float4(d.x * p.x * act_grad_from_output(e.x, cand_act), d.y * p.y * act_grad_from_output(e.y, cand_act),
+                              d.z * p.z * act_grad_from_output(e.z, cand_act), d.w * p.w * act_grad_from_output(e.w, cand_act));
       acc.x = fmaf(d.x, e.x, acc.x); acc.y = fmaf(d.y, e.y, acc.y); acc.z = fmaf(d.z, e.z, acc.z); acc.w = fmaf(d.w, e.w, acc.w);
     }
     d_pred[l * C4 + c] = acc;
@@ -174,12 +176,12 @@ extern "C" int nar_mul_pred(const float* cand, const float* pred, int64_t n_pos,
 }
 
 extern "C" int nar_mul_pred_bwd(const float* d_prod, const float* cand, const float* pred, int64_t n_pos, int64_t n_cand, int64_t C,
-                                float* d_cand, float* d_pred, void* stream) {
+                                int cand_act, float* d_cand, float* d_pred, void* stream) {
   if (!d_prod || !cand || !pred || !d_cand || !d_pred || (C & 3)) return NAR_ERR_INVALID;
   if (n_pos <= 0) return NAR_OK;
   nar::loss::mul_pred_bwd_kernel<<<(unsigned)n_pos, 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(d_prod), reinterpret_cast<const float4*>(cand), reinterpret_cast<const float4*>(pred), n_cand,
-      (int)(C / 4), reinterpret_cast<float4*>(d_cand), reinterpret_cast<float4*>(d_pred));
+      (int)(C / 4), cand_act, reinterpret_cast<float4*>(d_cand), reinterpret_cast<float4*>(d_pred));
   NAR_LAUNCH_CHECK();
   return NAR_OK;
 }

@@ -53,6 +53,35 @@ __device__ void bitonic_sort(uint64_t* a, uint32_t n) {
   }
 }
 
+// bitonic sort of exactly blockDim.x (= 1024) keys, one per thread, a[] in shared memory (in and out).
+// Compare-exchange distances below 32 stay inside a warp (shuffles, no barrier): 15 block barriers instead of 55.
+__device__ void bitonic_sort_block1024(uint64_t* a, uint64_t* scratch /*[1024]*/) {
+  const uint32_t i = threadIdx.x;
+  uint64_t x = a[i];
+  uint64_t* bufs[2] = {a, scratch};
+  int cur = 0;
+  for (uint32_t k = 2; k <= 1024u; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      uint64_t y;
+      if (j >= 32u) {
+        bufs[cur][i] = x;
+        __syncthreads();
+        y = bufs[cur][i ^ j];
+        cur ^= 1;                     // next exchange writes the other buffer: no second barrier needed
+      } else {
+        y = __shfl_xor_sync(0xffffffffu, x, (int)j);
+      }
+      const bool up = (i & k) == 0;
+      const bool lower = (i & j) == 0;
+      const uint64_t mn = x < y ? x : y, mx = x < y ? y : x;
+      x = (lower == up) ? mn : mx;
+    }
+  }
+  __syncthreads();
+  a[i] = x;
+  __syncthreads();
+}
+
 // exclusive block scan of one int per thread (blockDim.x <= 1024); returns the exclusive prefix, total in *total
 __device__ int block_exclusive_scan(int v, int* sh /*[33]*/, int* total) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -187,7 +216,13 @@ pool_kernel(const int64_t* __restrict__ all_items, int64_t NB, const int64_t* __
     if (key <= thr2) sort_buf[atomicAdd(&s_count, 1)] = key;    // exactly n_pool keys (keys are unique)
   }
   __syncthreads();
-  bitonic_sort(sort_buf, np2);
+  if (np2 <= 1024u) {                       // common case (K*20 <= 1024): register / shuffle bitonic network
+    for (uint32_t i = np2 + t; i < 1024u; i += POOL_THREADS) sort_buf[i] = KEY_MAX;
+    __syncthreads();
+    bitonic_sort_block1024(sort_buf, sort_buf + 1024);
+  } else {
+    bitonic_sort(sort_buf, np2);
+  }
   for (int i = t; i < n_pool; i += POOL_THREADS) {
     const uint64_t key = sort_buf[i];
     const int64_t ident = (int64_t)(key & 0xFFFFFFFFull);
@@ -200,7 +235,13 @@ pool_kernel(const int64_t* __restrict__ all_items, int64_t NB, const int64_t* __
   for (uint32_t i = t; i < np2; i += POOL_THREADS)
     sort_buf[i] = i < (uint32_t)n_pool ? (((uint64_t)ws.pool_item[i] << 20) | (uint64_t)i) : KEY_MAX;
   __syncthreads();
-  bitonic_sort(sort_buf, np2);
+  if (np2 <= 1024u) {
+    for (uint32_t i = np2 + t; i < 1024u; i += POOL_THREADS) sort_buf[i] = KEY_MAX;
+    __syncthreads();
+    bitonic_sort_block1024(sort_buf, sort_buf + 1024);
+  } else {
+    bitonic_sort(sort_buf, np2);
+  }
   // heads of runs -> unique index (contiguous chunk per thread keeps order)
   const int chunk = (n_pool + POOL_THREADS - 1) / POOL_THREADS;
   const int lo = min(n_pool, t * chunk), hi = min(n_pool, lo + chunk);
@@ -307,7 +348,7 @@ extern "C" int nar_sample_negatives(nar_ctx* ctx, const int64_t* all_items_globa
   int rc = carve(workspace, workspace_bytes, Bg * T1, buf_len, cap, &ws, &need);
   if (rc) return rc;
   uint32_t np2 = 1; while (np2 < (uint32_t)cap) np2 <<= 1;
-  const size_t smem = (size_t)np2 * 8;
+  const size_t smem = (size_t)(np2 < 2048u ? 2048u : np2) * 8;     // pool kernel: 1024 keys + 1024 scratch at least
   static bool attr_set = false;
   if (!attr_set) {
     NAR_CHECK_CUDA(cudaFuncSetAttribute(pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_POOL * 8));

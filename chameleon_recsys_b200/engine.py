@@ -384,9 +384,9 @@ class NarEngine:
             self._dgrad(dZ2, 'M2', dZ1, Rc, dact=ACT_LEAKY, aux=Z1)
             self._wgrad(PD, dZ1, 'M1', Rc); self._bgrad(dZ1, 'c1', Rc, 128)
             self._dgrad(dZ1, 'M1', PD, Rc)                       # d(prod) over PD in place (wgrad was issued first)
-            ops.mul_pred_bwd(PD, Ec, PR, L, n_cand, C_, dE[L:], dPR)
-        # candidate rows: through the CAR tanh
-        ops.act_bwd(dE[L:], Ec, Rc * C_, ACT_TANH, dE[L:])
+            ops.mul_pred_bwd(PD, Ec, PR, L, n_cand, C_, dE[L:], dPR, cand_act=ACT_TANH)   # candidate rows: through the CAR tanh
+        else:
+            ops.act_bwd(dE[L:], Ec, Rc * C_, ACT_TANH, dE[L:])
         # FC2 / FC1 (nar_model.py:410-426)
         ops.act_bwd(dPR, PR, L * C_, ACT_TANH, dPR)
         self._wgrad(F1, dPR, 'W4', L); self._bgrad(dPR, 'b4', L, C_)

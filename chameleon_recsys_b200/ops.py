@@ -146,10 +146,10 @@ def mul_pred(cand, pred, n_pos, n_cand, Cdim, prod):
     check(_lib.load().nar_mul_pred(_p(cand), _p(pred), n_pos, n_cand, Cdim, _p(prod), _stream()), 'nar_mul_pred')
 
 
-def mul_pred_bwd(d_prod, cand, pred, n_pos, n_cand, Cdim, d_cand, d_pred):
+def mul_pred_bwd(d_prod, cand, pred, n_pos, n_cand, Cdim, d_cand, d_pred, cand_act=ACT_NONE):
     global LAUNCHES
     LAUNCHES += 1
-    check(_lib.load().nar_mul_pred_bwd(_p(d_prod), _p(cand), _p(pred), n_pos, n_cand, Cdim, _p(d_cand), _p(d_pred), _stream()),
+    check(_lib.load().nar_mul_pred_bwd(_p(d_prod), _p(cand), _p(pred), n_pos, n_cand, Cdim, cand_act, _p(d_cand), _p(d_pred), _stream()),
           'nar_mul_pred_bwd')
 
 

@@ -182,9 +182,10 @@ int nar_sample_negatives(nar_ctx* ctx, const int64_t* all_items_global, int64_t 
 /* prod[r,:] = cand[r,:] * pred[r / n_cand,:]   (tf.multiply nar_model.py:478,:493)          */
 int nar_mul_pred(const float* cand, const float* pred, int64_t n_pos, int64_t n_cand, int64_t C,
                  float* prod, void* stream);
-/* d_cand = d_prod*pred ; d_pred[l] = sum_j d_prod[l,j]*cand[l,j]                            */
+/* d_cand = d_prod*pred*act'(cand) ; d_pred[l] = sum_j d_prod[l,j]*cand[l,j].  cand_act (nar_act): the
+ * activation that produced cand (the CAR tanh) is differentiated in the same pass; NAR_ACT_NONE = plain product rule */
 int nar_mul_pred_bwd(const float* d_prod, const float* cand, const float* pred, int64_t n_pos, int64_t n_cand,
-                     int64_t C, float* d_cand, float* d_pred, void* stream);
+                     int64_t C, int cand_act, float* d_cand, float* d_pred, void* stream);
 /* last Dense(32->1) + /temperature + log-softmax over the 1+K candidates + masked mean CE,
  * forward and backward in one pass.  z3 [n_pos*n_cand, ld_z] ; logits [n_pos,n_cand] ;
  * loss_sum += sum_l -(logp[l,0]) * inv_count ; d_z3 = d(loss)/d(z3) (before leaky');

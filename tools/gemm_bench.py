@@ -38,6 +38,7 @@ def main():
     dY = torch.randn(M, N, device=dev)
     dW = torch.zeros(K, N, device=dev)
     bias = torch.zeros(N, device=dev)
+    X2 = torch.randn(M, K, device=dev)
     Wlo = torch.empty_like(W)
     ops.tf32_lo(W, W.numel(), Wlo)
     cases = [
@@ -45,6 +46,8 @@ def main():
         ('fwd  3x  A:K  B:MN', lambda: ops.gemm(X, W, Y, M, N, K, a_kmajor=True, b_kmajor=False, bias=bias, act=2, precision=3), 2.0 * M * N * K),
         ('fwd  1x  A:K  B:MN', lambda: ops.gemm(X, W, Y, M, N, K, a_kmajor=True, b_kmajor=False, bias=bias, act=2, precision=1), 2.0 * M * N * K),
         ('dgrad 1x A:K  B:K ', lambda: ops.gemm(dY, W, Y, M, K, N, a_kmajor=True, b_kmajor=True, precision=1), 2.0 * M * N * K),
+        ('dgrad 1x +dact aux sep', lambda: ops.gemm(dY, W, Y, M, K, N, a_kmajor=True, b_kmajor=True, precision=1, dact=1, aux=X), 2.0 * M * N * K),
+        ('dgrad 1x +dact in place', lambda: ops.gemm(dY, W, X2, M, K, N, a_kmajor=True, b_kmajor=True, precision=1, dact=1, aux=X2), 2.0 * M * N * K),
         ('wgrad 1x A:MN B:MN', lambda: ops.gemm(X, dY, dW, K, N, M, a_kmajor=False, b_kmajor=False, accumulate=True, split_k=0, precision=1), 2.0 * M * N * K),
     ]
     for name, fn, flops in cases:

@@ -32,6 +32,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
+
+
 def _peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -173,7 +182,7 @@ def run_reference(args):
                              'sample': '%d full train steps of the same global batch (%d sessions) on the torch-CPU oracle; '
                                        'TF1.12 itself cannot be installed (python 3.12, no network)' % (args.steps, gb)},
             'e2e': {'value': v, 'unit': 'interactions/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -316,7 +325,7 @@ def run_ours(args):
             'roofline': roof, 'roofline_gather': roof_g, 'clocks': clocks}
     if cpu:
         line['cpu_baseline'] = cpu
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -393,6 +402,11 @@ def main():
     ap.add_argument('--cpu-steps', type=int, default=5)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
+    # the contract is ONE JSON line on stdout: libraries (NCCL prints its version banner there) get stderr instead
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3
     if args.impl == 'reference':

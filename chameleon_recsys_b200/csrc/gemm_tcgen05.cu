@@ -39,18 +39,24 @@ constexpr int NUM_THREADS = 256;
 
 // Two shared-memory rings.  The operand ring (TMA destination) is deep to hide TMA latency; the 3xTF32 "lo"
 // tiles only live from the split to the MMAs that consume them, so their ring is shallow.
+//   MODE 3: 3x with the A operand in TENSOR MEMORY (tcgen05.mma TS form): the split warps read the TMA tile once
+//           and write A_hi | A_lo into TMEM (tcgen05.st); the MMAs then read only B / B_lo from shared memory.
+//           (MODE 2 re-reads the A slices from shared memory for each of the 3 MMAs and is bound by the shared-
+//           memory port: ~176 KB of smem traffic per k-tile vs ~112 KB here.)  Needs A K-major and a B_lo plane.
 template <int MODE, int T> struct Cfg {
   static constexpr bool SPLIT3 = MODE != 0;
-  static constexpr bool BLO = MODE == 2;
+  static constexpr bool BLO = MODE >= 2;
+  static constexpr bool ATMEM = MODE == 3;
   static constexpr int A_BYTES = T * TILE_BYTES_1;
   static constexpr int B_BYTES = T * TILE_BYTES_1;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES * (BLO ? 2 : 1);     // one operand stage (A | B [| B_lo])
-  static constexpr int LO_STAGE_BYTES = SPLIT3 ? (BLO ? A_BYTES : A_BYTES + B_BYTES) : 0;
+  static constexpr int LO_STAGE_BYTES = (SPLIT3 && !ATMEM) ? (BLO ? A_BYTES : A_BYTES + B_BYTES) : 0;
   static constexpr int STAGES = SPLIT3 ? (BLO ? 4 : 5) : (T == 2 ? 3 : 6);  // operand ring depth
-  static constexpr int LO_STAGES = SPLIT3 ? 2 : 0;
-  static constexpr int TILE_BYTES = STAGES * STAGE_BYTES + LO_STAGES * LO_STAGE_BYTES;
+  static constexpr int LO_STAGES = SPLIT3 ? (ATMEM ? 4 : 2) : 0;            // lo ring depth (shared memory, or TMEM for MODE 3)
+  static constexpr int TILE_BYTES = STAGES * STAGE_BYTES + (ATMEM ? 0 : LO_STAGES * LO_STAGE_BYTES);
   static constexpr int SMEM_BYTES = TILE_BYTES + 256 + 1024;                // tiles + barriers + align slack
-  static constexpr int TMEM_COLS = T * T * 128;                             // 128 or 512
+  static constexpr int TMEM_COLS = ATMEM ? 512 : T * T * 128;               // accumulators (+ 4 x (A_hi | A_lo) of 32 columns each)
+  static constexpr int TMEM_A_BASE = 128;                                   // MODE 3: A ring starts after the accumulator
   static_assert(T == 1 || MODE == 0, "256x256 tiles only in single-pass mode (shared memory)");
 };
 
@@ -118,6 +124,25 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand from tensor memory (TS form): D[tmem] (+)= A[tmem, 128 lanes x 8 columns] * B[smem]
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -211,7 +236,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_blo, const Params p) {
   using C = Cfg<MODE, T>;
-  constexpr bool SPLIT3 = C::SPLIT3, BLO = C::BLO;
+  constexpr bool SPLIT3 = C::SPLIT3, BLO = C::BLO, ATMEM = C::ATMEM;
+  constexpr int LS = C::LO_STAGES > 0 ? C::LO_STAGES : 1;        // lo ring depth (2 in shared memory, 4 in TMEM)
+  static_assert(!ATMEM || !A_MN, "A in tensor memory must be K-major");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -220,10 +247,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::TILE_BYTES);
   uint64_t* full = bars;                          // [STAGES]    TMA landed
   uint64_t* empty = bars + C::STAGES;             // [STAGES]    MMAs that read the operand stage retired
-  uint64_t* xf = bars + 2 * C::STAGES;            // [2] lo tiles written (128 arrivals)
-  uint64_t* lo_empty = xf + 2;                    // [2] MMAs that read the lo stage retired
-  uint64_t* tmem_full = xf + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xf + 5);
+  uint64_t* xf = bars + 2 * C::STAGES;            // [4] lo tiles written (128 arrivals)
+  uint64_t* lo_empty = xf + 4;                    // [4] MMAs that read the lo stage retired
+  uint64_t* tmem_full = xf + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xf + 9);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -241,9 +268,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp_idx == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], ATMEM ? 129 : 1);      // MODE 3: the A tile is released by the 128 split threads, B by the MMA commit
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 4; ++s) {
       mbar_init(&xf[s], 128);
       mbar_init(&lo_empty[s], 1);
     }
@@ -281,14 +308,28 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       for (int kt = 0; kt < num_kt; ++kt) {
         const int s = kt % C::STAGES;
         const uint32_t ph = (uint32_t)(kt / C::STAGES) & 1u;
-        const int ls = SPLIT3 ? (kt % 2) : 0;
+        const int ls = SPLIT3 ? (kt % LS) : 0;
         mbar_wait(&full[s], ph);
-        if (SPLIT3) mbar_wait(&xf[ls], (uint32_t)(kt / 2) & 1u);
+        if (SPLIT3) mbar_wait(&xf[ls], (uint32_t)(kt / LS) & 1u);
         tc_fence_after();
         const uint32_t a_hi = smem_u32(tiles + s * C::STAGE_BYTES);
         const uint32_t b_hi = a_hi + C::A_BYTES;
         const uint32_t a_lo = smem_u32(lo_tiles + ls * C::LO_STAGE_BYTES);
         const uint32_t b_lo = BLO ? (b_hi + C::B_BYTES) : (a_lo + C::A_BYTES);
+        if (ATMEM) {
+          const uint32_t ta_hi = tmem_base + (uint32_t)(C::TMEM_A_BASE + ls * 64);      // 32 columns A_hi | 32 columns A_lo
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t db = make_smem_desc<B_MN>(b_hi + k * b_kstep);
+            const uint64_t dbl = make_smem_desc<B_MN>(b_lo + k * b_kstep);
+            umma_tf32_ts(tmem_base, ta_hi + 32 + k * UMMA_K, db, idesc, (kt > 0 || k > 0) ? 1u : 0u);   // A_lo * B_hi
+            umma_tf32_ts(tmem_base, ta_hi + k * UMMA_K, dbl, idesc, 1u);                                  // A_hi * B_lo
+            umma_tf32_ts(tmem_base, ta_hi + k * UMMA_K, db, idesc, 1u);                                   // A_hi * B_hi
+          }
+          umma_commit(&empty[s]);
+          umma_commit(&lo_empty[ls]);
+          continue;
+        }
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
           const uint64_t db = make_smem_desc<B_MN>(b_hi + k * b_kstep);
@@ -322,14 +363,37 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       for (int kt = 0; kt < num_kt; ++kt) {
         const int s = kt % C::STAGES;
         const uint32_t ph = (uint32_t)(kt / C::STAGES) & 1u;
-        const int ls = kt % 2;
-        mbar_wait(&lo_empty[ls], ((uint32_t)(kt / 2) & 1u) ^ 1u);     // MMAs of k-tile kt-2 no longer read this lo stage
+        const int ls = kt % LS;
+        mbar_wait(&lo_empty[ls], ((uint32_t)(kt / LS) & 1u) ^ 1u);    // MMAs of k-tile kt-LS no longer read this lo stage
         mbar_wait(&full[s], ph);
+        if (ATMEM) {
+          // thread = accumulator lane = A row: read the row's 32 k-values (8 swizzled 16-byte chunks) from the TMA tile
+          // and write A_hi | A_lo into tensor memory; the MMAs never touch the A tile in shared memory
+          const int row = ew * 32 + lane;
+          const uint8_t* arow = tiles + s * C::STAGE_BYTES + row * 128;
+          uint32_t hi_r[32], lo_r[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7)) << 4));
+            hi_r[4 * c + 0] = __float_as_uint(v.x); hi_r[4 * c + 1] = __float_as_uint(v.y);
+            hi_r[4 * c + 2] = __float_as_uint(v.z); hi_r[4 * c + 3] = __float_as_uint(v.w);
+            lo_r[4 * c + 0] = __float_as_uint(tf32_lo(v.x)); lo_r[4 * c + 1] = __float_as_uint(tf32_lo(v.y));
+            lo_r[4 * c + 2] = __float_as_uint(tf32_lo(v.z)); lo_r[4 * c + 3] = __float_as_uint(tf32_lo(v.w));
+          }
+          const uint32_t ta = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(C::TMEM_A_BASE + ls * 64);
+          tmem_st_32x32b_x32(ta, hi_r);
+          tmem_st_32x32b_x32(ta + 32, lo_r);
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(&xf[ls]);
+          mbar_arrive(&empty[s]);        // this thread is done with the A tile of the operand stage
+          continue;
+        }
         const float4* hi = reinterpret_cast<const float4*>(tiles + s * C::STAGE_BYTES);
         float4* lo = reinterpret_cast<float4*>(lo_tiles + ls * C::LO_STAGE_BYTES);
         // A (and, without a B_lo plane in HBM, B: the two tiles are contiguous) -> lo.  All loads are issued
         // before the first use so the split costs one shared-memory round trip per k-tile.
-        constexpr int NV = SPLIT3 ? C::LO_STAGE_BYTES / 16 / 128 : 1;   // float4 per thread: 8 (A only) or 16 (A and B)
+        constexpr int NV = (SPLIT3 && !ATMEM) ? C::LO_STAGE_BYTES / 16 / 128 : 1;   // float4 per thread: 8 (A only) or 16 (A and B)
         float4 v[NV];
 #pragma unroll
         for (int i = 0; i < NV; ++i) v[i] = hi[te + i * 128];
@@ -441,7 +505,7 @@ extern "C" int nar_gemm_tf32(nar_ctx* ctx, int64_t M, int64_t N, int64_t K, cons
   if (epi->dact && (!epi->aux || (epi->ld_aux & 3) != 0 || (reinterpret_cast<uintptr_t>(epi->aux) & 15u) != 0)) return NAR_ERR_INVALID;
   if (epi->precision != 1 && epi->precision != 3) return NAR_ERR_INVALID;
   const bool blo = epi->precision == 3 && epi->b_lo != nullptr;
-  const int mode = epi->precision == 1 ? 0 : (blo ? 2 : 1);
+  const int mode = epi->precision == 1 ? 0 : (blo ? (a_kmajor ? 3 : 2) : 1);
   // 256x256 CTA tiles for the big single-pass GEMMs (L2-bound with 128x128 tiles); 128x128 otherwise
   const int T = (mode == 0 && M >= 256 && N >= 256 && (double)M * (double)N * (double)K >= 4e9) ? 2 : 1;
   const int64_t n_tiles = (N + BN * T - 1) / (BN * T), m_tiles = (M + BM * T - 1) / (BM * T);
@@ -484,6 +548,7 @@ extern "C" int nar_gemm_tf32(nar_ctx* ctx, int64_t M, int64_t N, int64_t K, cons
     if (mode == 0 && T == 2) return launch<a, b, 0, 2>(ta, tb, tbl, p, grid, st); \
     if (mode == 1) return launch<a, b, 1, 1>(ta, tb, tbl, p, grid, st); \
     if (mode == 2) return launch<a, b, 2, 1>(ta, tb, tbl, p, grid, st); \
+    if (mode == 3) return launch<false, b, 3, 1>(ta, tb, tbl, p, grid, st); \
   }
   NAR_GEMM_CASE(false, false) NAR_GEMM_CASE(false, true) NAR_GEMM_CASE(true, false) NAR_GEMM_CASE(true, true)
 #undef NAR_GEMM_CASE

@@ -43,21 +43,22 @@ constexpr int NUM_THREADS = 256;
 //           and write A_hi | A_lo into TMEM (tcgen05.st); the MMAs then read only B / B_lo from shared memory.
 //           (MODE 2 re-reads the A slices from shared memory for each of the 3 MMAs and is bound by the shared-
 //           memory port: ~176 KB of smem traffic per k-tile vs ~112 KB here.)  Needs A K-major and a B_lo plane.
-template <int MODE, int T> struct Cfg {
+template <int MODE, int TM, int TN> struct Cfg {
   static constexpr bool SPLIT3 = MODE != 0;
   static constexpr bool BLO = MODE >= 2;
   static constexpr bool ATMEM = MODE == 3;
-  static constexpr int A_BYTES = T * TILE_BYTES_1;
-  static constexpr int B_BYTES = T * TILE_BYTES_1;
+  static constexpr int A_BYTES = TM * TILE_BYTES_1;
+  static constexpr int B_BYTES = TN * TILE_BYTES_1;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES * (BLO ? 2 : 1);     // one operand stage (A | B [| B_lo])
   static constexpr int LO_STAGE_BYTES = (SPLIT3 && !ATMEM) ? (BLO ? A_BYTES : A_BYTES + B_BYTES) : 0;
-  static constexpr int STAGES = SPLIT3 ? (BLO ? 4 : 5) : (T == 2 ? 3 : 6);  // operand ring depth
-  static constexpr int LO_STAGES = SPLIT3 ? (ATMEM ? 4 : 2) : 0;            // lo ring depth (shared memory, or TMEM for MODE 3)
+  static constexpr int STAGES = SPLIT3 ? (BLO ? (TM == 2 ? 3 : 4) : 5) : (TM * TN == 4 ? 3 : 6);  // operand ring depth
+  static constexpr int LO_STAGES = SPLIT3 ? (ATMEM ? (TM == 2 ? 2 : 4) : 2) : 0;   // lo ring depth (shared memory, or TMEM for MODE 3)
   static constexpr int TILE_BYTES = STAGES * STAGE_BYTES + (ATMEM ? 0 : LO_STAGES * LO_STAGE_BYTES);
   static constexpr int SMEM_BYTES = TILE_BYTES + 256 + 1024;                // tiles + barriers + align slack
-  static constexpr int TMEM_COLS = ATMEM ? 512 : T * T * 128;               // accumulators (+ 4 x (A_hi | A_lo) of 32 columns each)
-  static constexpr int TMEM_A_BASE = 128;                                   // MODE 3: A ring starts after the accumulator
-  static_assert(T == 1 || MODE == 0, "256x256 tiles only in single-pass mode (shared memory)");
+  static constexpr int TMEM_COLS = ATMEM ? 512 : TM * TN * 128;             // accumulators (+ A ring: TM x (A_hi | A_lo) of 32 columns per stage)
+  static constexpr int TMEM_A_BASE = TM * TN * 128;                         // MODE 3: A ring starts after the accumulators
+  static_assert((TM == 1 && TN == 1) || MODE == 0 || (MODE == 3 && TM == 2 && TN == 1), "tile shapes: 128x128; 256x256 single pass; 256x128 with A in TMEM");
+  static_assert(!ATMEM || TMEM_A_BASE + LO_STAGES * TM * 64 <= 512, "tensor memory budget");
 };
 
 struct Params {
@@ -231,11 +232,11 @@ __device__ __forceinline__ void load_operand(uint32_t dst, const CUtensorMap* ma
 }
 
 // ---------------------------------------------------------------- kernel
-template <bool A_MN, bool B_MN, int MODE, int T>
+template <bool A_MN, bool B_MN, int MODE, int TM, int TN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_blo, const Params p) {
-  using C = Cfg<MODE, T>;
+  using C = Cfg<MODE, TM, TN>;
   constexpr bool SPLIT3 = C::SPLIT3, BLO = C::BLO, ATMEM = C::ATMEM;
   constexpr int LS = C::LO_STAGES > 0 ? C::LO_STAGES : 1;        // lo ring depth (2 in shared memory, 4 in TMEM)
   static_assert(!ATMEM || !A_MN, "A in tensor memory must be K-major");
@@ -294,15 +295,15 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int k_elem = (kt0 + kt) * BK;
         const uint32_t a_dst = smem_u32(tiles + s * C::STAGE_BYTES);
         const uint32_t b_dst = a_dst + C::A_BYTES;
-        load_operand<A_MN, T>(a_dst, &tmap_a, &full[s], m_blk * BM * T, k_elem);
-        load_operand<B_MN, T>(b_dst, &tmap_b, &full[s], n_blk * BN * T, k_elem);
-        if (BLO) load_operand<B_MN, T>(b_dst + C::B_BYTES, &tmap_blo, &full[s], n_blk * BN * T, k_elem);
+        load_operand<A_MN, TM>(a_dst, &tmap_a, &full[s], m_blk * BM * TM, k_elem);
+        load_operand<B_MN, TN>(b_dst, &tmap_b, &full[s], n_blk * BN * TN, k_elem);
+        if (BLO) load_operand<B_MN, TN>(b_dst + C::B_BYTES, &tmap_blo, &full[s], n_blk * BN * TN, k_elem);
       }
     }
   } else if (warp_idx == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      constexpr uint32_t idesc = make_idesc_n<A_MN, B_MN, BN * T>();
+      constexpr uint32_t idesc = make_idesc_n<A_MN, B_MN, BN * TN>();
       constexpr uint32_t a_kstep = A_MN ? 1024u : (uint32_t)(UMMA_K * 4);
       constexpr uint32_t b_kstep = B_MN ? 1024u : (uint32_t)(UMMA_K * 4);
       for (int kt = 0; kt < num_kt; ++kt) {
@@ -317,14 +318,18 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const uint32_t a_lo = smem_u32(lo_tiles + ls * C::LO_STAGE_BYTES);
         const uint32_t b_lo = BLO ? (b_hi + C::B_BYTES) : (a_lo + C::A_BYTES);
         if (ATMEM) {
-          const uint32_t ta_hi = tmem_base + (uint32_t)(C::TMEM_A_BASE + ls * 64);      // 32 columns A_hi | 32 columns A_lo
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t db = make_smem_desc<B_MN>(b_hi + k * b_kstep);
             const uint64_t dbl = make_smem_desc<B_MN>(b_lo + k * b_kstep);
-            umma_tf32_ts(tmem_base, ta_hi + 32 + k * UMMA_K, db, idesc, (kt > 0 || k > 0) ? 1u : 0u);   // A_lo * B_hi
-            umma_tf32_ts(tmem_base, ta_hi + k * UMMA_K, dbl, idesc, 1u);                                  // A_hi * B_lo
-            umma_tf32_ts(tmem_base, ta_hi + k * UMMA_K, db, idesc, 1u);                                   // A_hi * B_hi
+#pragma unroll
+            for (int tm = 0; tm < TM; ++tm) {
+              const uint32_t acc = tmem_base + (uint32_t)(tm * BN * TN);
+              const uint32_t ta_hi = tmem_base + (uint32_t)(C::TMEM_A_BASE + (ls * TM + tm) * 64);   // 32 columns A_hi | 32 columns A_lo
+              umma_tf32_ts(acc, ta_hi + 32 + k * UMMA_K, db, idesc, (kt > 0 || k > 0) ? 1u : 0u);    // A_lo * B_hi
+              umma_tf32_ts(acc, ta_hi + k * UMMA_K, dbl, idesc, 1u);                                   // A_hi * B_lo
+              umma_tf32_ts(acc, ta_hi + k * UMMA_K, db, idesc, 1u);                                    // A_hi * B_hi
+            }
           }
           umma_commit(&empty[s]);
           umma_commit(&lo_empty[ls]);
@@ -334,8 +339,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int k = 0; k < BK / UMMA_K; ++k) {
           const uint64_t db = make_smem_desc<B_MN>(b_hi + k * b_kstep);
 #pragma unroll
-          for (int tm = 0; tm < T; ++tm) {
-            const uint32_t acc = tmem_base + (uint32_t)(tm * BN * T);          // accumulator tm: columns [tm*128*T, ...)
+          for (int tm = 0; tm < TM; ++tm) {
+            const uint32_t acc = tmem_base + (uint32_t)(tm * BN * TN);         // accumulator tm: columns [tm*128*TN, ...)
             const uint32_t a_tm = a_hi + tm * TILE_BYTES_1 + k * a_kstep;       // MN-major: 4 boxes of 4096 B = TILE_BYTES_1
             const uint64_t da = make_smem_desc<A_MN>(a_tm);
             const uint32_t first = (kt > 0 || k > 0) ? 1u : 0u;
@@ -369,20 +374,23 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (ATMEM) {
           // thread = accumulator lane = A row: read the row's 32 k-values (8 swizzled 16-byte chunks) from the TMA tile
           // and write A_hi | A_lo into tensor memory; the MMAs never touch the A tile in shared memory
-          const int row = ew * 32 + lane;
-          const uint8_t* arow = tiles + s * C::STAGE_BYTES + row * 128;
-          uint32_t hi_r[32], lo_r[32];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7)) << 4));
-            hi_r[4 * c + 0] = __float_as_uint(v.x); hi_r[4 * c + 1] = __float_as_uint(v.y);
-            hi_r[4 * c + 2] = __float_as_uint(v.z); hi_r[4 * c + 3] = __float_as_uint(v.w);
-            lo_r[4 * c + 0] = __float_as_uint(tf32_lo(v.x)); lo_r[4 * c + 1] = __float_as_uint(tf32_lo(v.y));
-            lo_r[4 * c + 2] = __float_as_uint(tf32_lo(v.z)); lo_r[4 * c + 3] = __float_as_uint(tf32_lo(v.w));
+          for (int tm = 0; tm < TM; ++tm) {
+            const int row = tm * 128 + ew * 32 + lane;
+            const uint8_t* arow = tiles + s * C::STAGE_BYTES + row * 128;
+            uint32_t hi_r[32], lo_r[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7)) << 4));
+              hi_r[4 * c + 0] = __float_as_uint(v.x); hi_r[4 * c + 1] = __float_as_uint(v.y);
+              hi_r[4 * c + 2] = __float_as_uint(v.z); hi_r[4 * c + 3] = __float_as_uint(v.w);
+              lo_r[4 * c + 0] = __float_as_uint(tf32_lo(v.x)); lo_r[4 * c + 1] = __float_as_uint(tf32_lo(v.y));
+              lo_r[4 * c + 2] = __float_as_uint(tf32_lo(v.z)); lo_r[4 * c + 3] = __float_as_uint(tf32_lo(v.w));
+            }
+            const uint32_t ta = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(C::TMEM_A_BASE + (ls * TM + tm) * 64);
+            tmem_st_32x32b_x32(ta, hi_r);
+            tmem_st_32x32b_x32(ta + 32, lo_r);
           }
-          const uint32_t ta = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(C::TMEM_A_BASE + ls * 64);
-          tmem_st_32x32b_x32(ta, hi_r);
-          tmem_st_32x32b_x32(ta + 32, lo_r);
           tmem_wait_st();
           tc_fence_before();
           mbar_arrive(&xf[ls]);
@@ -415,13 +423,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     float* stage = reinterpret_cast<float*>(tiles) + ew * (32 * STAGE_LD);
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;
 #pragma unroll
-    for (int tm = 0; tm < T; ++tm) {
-      const int64_t row_base = ((int64_t)m_blk * T + tm) * BM + ew * 32;
-      for (int c = 0; c < BN * T; c += 32) {
-        const int64_t col0 = (int64_t)n_blk * BN * T + c;
+    for (int tm = 0; tm < TM; ++tm) {
+      const int64_t row_base = ((int64_t)m_blk * TM + tm) * BM + ew * 32;
+      for (int c = 0; c < BN * TN; c += 32) {
+        const int64_t col0 = (int64_t)n_blk * BN * TN + c;
         if (col0 >= p.N) break;               // warp-uniform
         uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(tm * BN * T + c), r);
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(tm * BN * TN + c), r);
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
           *reinterpret_cast<float4*>(stage + lane * STAGE_LD + j) =
@@ -477,15 +485,15 @@ static int make_operand_map(const nar_ctx* ctx, CUtensorMap* map, const float* p
   return r == CUDA_SUCCESS ? NAR_OK : NAR_ERR_INVALID;
 }
 
-template <bool A_MN, bool B_MN, int MODE, int T>
+template <bool A_MN, bool B_MN, int MODE, int TM, int TN>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbl, const Params& p, dim3 grid, cudaStream_t st) {
-  auto kern = gemm_tf32_kernel<A_MN, B_MN, MODE, T>;
+  auto kern = gemm_tf32_kernel<A_MN, B_MN, MODE, TM, TN>;
   static bool attr_set = false;     // per instantiation
   if (!attr_set) {
-    NAR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE, T>::SMEM_BYTES));
+    NAR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE, TM, TN>::SMEM_BYTES));
     attr_set = true;
   }
-  kern<<<grid, NUM_THREADS, Cfg<MODE, T>::SMEM_BYTES, st>>>(ta, tb, tbl, p);
+  kern<<<grid, NUM_THREADS, Cfg<MODE, TM, TN>::SMEM_BYTES, st>>>(ta, tb, tbl, p);
   NAR_LAUNCH_CHECK();
   return NAR_OK;
 }
@@ -507,8 +515,10 @@ extern "C" int nar_gemm_tf32(nar_ctx* ctx, int64_t M, int64_t N, int64_t K, cons
   const bool blo = epi->precision == 3 && epi->b_lo != nullptr;
   const int mode = epi->precision == 1 ? 0 : (blo ? (a_kmajor ? 3 : 2) : 1);
   // 256x256 CTA tiles for the big single-pass GEMMs (L2-bound with 128x128 tiles); 128x128 otherwise
-  const int T = (mode == 0 && M >= 256 && N >= 256 && (double)M * (double)N * (double)K >= 4e9) ? 2 : 1;
-  const int64_t n_tiles = (N + BN * T - 1) / (BN * T), m_tiles = (M + BM * T - 1) / (BM * T);
+  const bool big = (double)M * (double)N * (double)K >= 4e9;
+  const int TM = ((mode == 0 && M >= 256 && N >= 256 && big) || (mode == 3 && M >= 1024 && big)) ? 2 : 1;
+  const int TN = (mode == 0 && TM == 2) ? 2 : 1;
+  const int64_t n_tiles = (N + BN * TN - 1) / (BN * TN), m_tiles = (M + BM * TM - 1) / (BM * TM);
   if (n_tiles * m_tiles > 0x7fffffffLL) return NAR_ERR_UNSUPPORTED;
   const int k_tiles = (int)((K + BK - 1) / BK);
   int split = epi->split_k;
@@ -526,13 +536,13 @@ extern "C" int nar_gemm_tf32(nar_ctx* ctx, int64_t M, int64_t N, int64_t K, cons
   int per = (k_tiles + split - 1) / split;
   split = (k_tiles + per - 1) / per;          // no empty splits
   CUtensorMap ta, tb;
-  int rc = make_operand_map(ctx, &ta, A, M, K, lda, a_kmajor != 0, T);
+  int rc = make_operand_map(ctx, &ta, A, M, K, lda, a_kmajor != 0, TM);
   if (rc) return rc;
-  rc = make_operand_map(ctx, &tb, B, N, K, ldb, b_kmajor != 0, T);
+  rc = make_operand_map(ctx, &tb, B, N, K, ldb, b_kmajor != 0, TN);
   if (rc) return rc;
   CUtensorMap tbl = tb;
   if (blo) {
-    rc = make_operand_map(ctx, &tbl, epi->b_lo, N, K, ldb, b_kmajor != 0, T);
+    rc = make_operand_map(ctx, &tbl, epi->b_lo, N, K, ldb, b_kmajor != 0, TN);
     if (rc) return rc;
   }
   Params p;
@@ -544,11 +554,12 @@ extern "C" int nar_gemm_tf32(nar_ctx* ctx, int64_t M, int64_t N, int64_t K, cons
   const bool amn = !a_kmajor, bmn = !b_kmajor;
 #define NAR_GEMM_CASE(a, b) \
   if (amn == a && bmn == b) { \
-    if (mode == 0 && T == 1) return launch<a, b, 0, 1>(ta, tb, tbl, p, grid, st); \
-    if (mode == 0 && T == 2) return launch<a, b, 0, 2>(ta, tb, tbl, p, grid, st); \
-    if (mode == 1) return launch<a, b, 1, 1>(ta, tb, tbl, p, grid, st); \
-    if (mode == 2) return launch<a, b, 2, 1>(ta, tb, tbl, p, grid, st); \
-    if (mode == 3) return launch<false, b, 3, 1>(ta, tb, tbl, p, grid, st); \
+    if (mode == 0 && TM == 1) return launch<a, b, 0, 1, 1>(ta, tb, tbl, p, grid, st); \
+    if (mode == 0 && TM == 2) return launch<a, b, 0, 2, 2>(ta, tb, tbl, p, grid, st); \
+    if (mode == 1) return launch<a, b, 1, 1, 1>(ta, tb, tbl, p, grid, st); \
+    if (mode == 2) return launch<a, b, 2, 1, 1>(ta, tb, tbl, p, grid, st); \
+    if (mode == 3 && TM == 1) return launch<false, b, 3, 1, 1>(ta, tb, tbl, p, grid, st); \
+    if (mode == 3 && TM == 2) return launch<false, b, 3, 2, 1>(ta, tb, tbl, p, grid, st); \
   }
   NAR_GEMM_CASE(false, false) NAR_GEMM_CASE(false, true) NAR_GEMM_CASE(true, false) NAR_GEMM_CASE(true, true)
 #undef NAR_GEMM_CASE

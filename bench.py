@@ -235,13 +235,20 @@ def run_ours(args):
     staged = [eng.stage(f, l, buf, pop, slot='bench%d' % i) for i, (f, l, buf, pop) in enumerate(batches[:n_total])]
     torch.cuda.synchronize()
 
-    def dev_step(st):
+    side = eng.side_stream()
+
+    def dev_step(i):
+        """step i on the main stream; the weight-independent front of step i+1 (sampler, row lists, statistics)
+        is queued on the side stream right behind it (the reference prefetches its next batch the same way)"""
+        st = staged[i]
         eng.grads.zero_()
         eng.step(st, train=True)
         eng.apply_gradients()
+        if i + 1 < len(staged):
+            eng.prepare(staged[i + 1], eng.global_step + 1, stream=side)
 
-    for st in staged[:args.warmup]:
-        dev_step(st)
+    for i in range(args.warmup):
+        dev_step(i)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -249,8 +256,8 @@ def run_ours(args):
     l0 = ops.LAUNCHES
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for st in staged[args.warmup:]:
-        dev_step(st)
+    for i in range(args.warmup, n_total):
+        dev_step(i)
     e1.record()
     barrier()
     launches = ops.LAUNCHES - l0

@@ -44,7 +44,7 @@ __device__ __forceinline__ float tanh_fast(float x) {
 
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == NAR_ACT_LEAKY_RELU) return leaky_relu(x);
-  if (act == NAR_ACT_TANH) return tanh_fast(x);
+  if (act == NAR_ACT_TANH) return tanhf(x);     // tanh_fast measured slower inside the GEMM epilogue (divergent branch)
   return x;
 }
 

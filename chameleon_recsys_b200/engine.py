@@ -91,6 +91,7 @@ class NarEngine:
         self._pinned: Dict[str, torch.Tensor] = {}
         self._sampler_ws = None
         self._planc_static = None
+        self._side = None
         self._views: dict = {}
         self.last: Dict[str, torch.Tensor] = {}
         self.ops = ops
@@ -156,7 +157,7 @@ class NarEngine:
 
     # ------------------------------------------------------------------ staging (host -> HBM, one copy)
     def stage(self, features: Dict[str, np.ndarray], labels: Dict[str, np.ndarray], buffer: np.ndarray,
-              pop_norm: np.ndarray, slot: str = 'stage') -> dict:
+              pop_norm: np.ndarray, slot: str = 'stage', stream: Optional[torch.cuda.Stream] = None) -> dict:
         """Pack the step inputs into one pinned buffer and issue one async H2D copy.
         ``features``/``labels`` hold the GLOBAL batch (all data-parallel ranks see the same arrays)."""
         item_clicked = np.ascontiguousarray(features['item_clicked'], dtype=np.int64)
@@ -191,14 +192,15 @@ class NarEngine:
             o, nel, _, _ = offs[name]
             pin_np[o:o + nel * np.dtype(dt).itemsize].view(dt)[:] = arr.reshape(-1)
         dev = self._buf(slot, total, 1, torch.uint8).view(-1)
-        dev[:total].copy_(pin[:total], non_blocking=True)
+        with torch.cuda.stream(stream if stream is not None else torch.cuda.current_stream()):
+            dev[:total].copy_(pin[:total], non_blocking=True)
         tmap = {np.int64: torch.int64, np.float32: torch.float32, np.int32: torch.int32}
         tens = {}
         for name, (o, nel, dt, shp) in offs.items():
             tens[name] = dev[o:o + nel * np.dtype(dt).itemsize].view(tmap[dt]).view(*shp) if nel > 0 else \
                 torch.zeros(shp, dtype=tmap[dt], device=self.dev)
         return {'t': tens, 'Bg': Bg, 'B': per, 'T': T, 'L': L, 'L_global': L_global, 's0': s0,
-                'h2d_bytes': total, 'lens': lens}
+                'h2d_bytes': total, 'lens': lens, 'slot': slot}
 
     # ------------------------------------------------------------------ feature plan for this step
     def _plan_c(self, st: dict) -> FeaturePlanC:
@@ -212,6 +214,7 @@ class NarEngine:
         for i, n in enumerate(self.plan.ctx_float_names):
             p.ctx_float[i] = t['cf/' + n].data_ptr()
         p.pop_norm = t['pop_norm'].data_ptr()
+        p.stats = st['stats'].data_ptr()
         return p
 
     def _plan_c_static(self) -> FeaturePlanC:
@@ -290,6 +293,44 @@ class NarEngine:
         ops.colsum_add(dY, rows, cols, dY.stride(0), self.view(bkey, self.grads).view(-1))
 
     # ------------------------------------------------------------------ the step
+    def prepare(self, st: dict, step_id: int, stream: Optional[torch.cuda.Stream] = None) -> dict:
+        """Everything of a step that does not depend on the weights: negatives (nar_model.py:265-276), the row
+        lists and the recency / novelty statistics.  May run one step AHEAD on a side stream (``stream``) while the
+        previous step's GEMMs occupy the SMs - the reference's tf.data prefetch(1) gives the same look-ahead
+        (datasets.py:142).  Results live in per-slot buffers and are handed over through a CUDA event."""
+        t = st['t']
+        B, Bg, T, L, s0 = st['B'], st['Bg'], st['T'], st['L'], st['s0']
+        K = self.K
+        n_cand = K + 1
+        R = L + L * n_cand
+        slot = st.get('slot', 'stage')
+        cur = torch.cuda.current_stream()
+        run_on = stream if stream is not None else cur
+        with torch.cuda.stream(run_on):
+            need = ops.sample_negatives_workspace(Bg, T + 1, self.buf_len, K)
+            if self._sampler_ws is None or self._sampler_ws.numel() < need:
+                self._sampler_ws = torch.zeros(need, dtype=torch.uint8, device=self.dev)
+            neg = self._buf('neg/' + slot, Bg * T, K, torch.int64)
+            if B < Bg:
+                neg.zero_()
+            neg_local = neg.view(-1)[s0 * T * K:(s0 + B) * T * K].view(B, T, K)
+            ops.sample_negatives(t['all_items'], s0, B, t['buffer'], K, self.n_from_buffer, self.seed, step_id, neg_local,
+                                 self._sampler_ws)
+            stats = self._buf('stats/' + slot, 24, 1).view(-1)
+            row_pos = self._buf('row_pos/' + slot, R, 1, torch.int32).view(-1)
+            row_item = self._buf('row_item/' + slot, R, 1, torch.int64).view(-1)
+            if L > 0:
+                ops.build_rows(t['pos_idx'], L, t['item_clicked'], t['label_next'], neg, K, row_pos, row_item)
+                ops.feature_stats(t['buffer'], self.n_norm, self.created_at, t['pop_norm'], t['max_ts'], self.lb_rec,
+                                  self.lb_nov, row_pos, row_item, R, L, n_cand, t['event_ts'], stats)
+            ev = None
+            if stream is not None:
+                ev = torch.cuda.Event()
+                ev.record(run_on)
+        st['prep'] = {'neg': neg, 'neg_local': neg_local, 'row_pos': row_pos, 'row_item': row_item, 'stats': stats,
+                      'event': ev, 'step_id': step_id}
+        return st
+
     def step(self, st: dict, train: bool = True, keep: bool = False) -> dict:
         """Run one step on staged inputs.  Returns device tensors (loss parts, logits, negatives)."""
         t = st['t']
@@ -301,26 +342,17 @@ class NarEngine:
         inv_count = 1.0 / max(1, st['L_global'])
         step_id = self.global_step + 1
         self.loss_dev.zero_()
-        # ---- negatives (nar_model.py:265-276)
-        need = ops.sample_negatives_workspace(Bg, T + 1, self.buf_len, K)
-        if self._sampler_ws is None or self._sampler_ws.numel() < need:
-            self._sampler_ws = torch.zeros(need, dtype=torch.uint8, device=self.dev)
-        neg = self._buf('neg', Bg * T, K, torch.int64)
-        if B < Bg:
-            neg.zero_()
-        neg_local = neg.view(-1)[s0 * T * K:(s0 + B) * T * K].view(B, T, K)
-        ops.sample_negatives(t['all_items'], s0, B, t['buffer'], K, self.n_from_buffer, self.seed, step_id, neg_local,
-                             self._sampler_ws)
+        prep = st.get('prep')
+        if prep is None or prep['step_id'] != step_id:
+            prep = self.prepare(st, step_id)['prep']          # inline, on the current stream
+        if prep['event'] is not None:
+            torch.cuda.current_stream().wait_event(prep['event'])
+        neg, neg_local, row_pos, row_item = prep['neg'], prep['neg_local'], prep['row_pos'], prep['row_item']
+        st['stats'] = prep['stats']
         out = {'negatives': neg_local, 'L': L}
         if L == 0:
             out.update(loss=self.loss_dev, logits=None)
             return out
-        # ---- row lists + features (nar_model.py:314-370)
-        row_pos = self._buf('row_pos', R, 1, torch.int32).view(-1)
-        row_item = self._buf('row_item', R, 1, torch.int64).view(-1)
-        ops.build_rows(t['pos_idx'], L, t['item_clicked'], t['label_next'], neg, K, row_pos, row_item)
-        ops.feature_stats(t['buffer'], self.n_norm, self.created_at, t['pop_norm'], t['max_ts'], self.lb_rec, self.lb_nov,
-                          row_pos, row_item, R, L, n_cand, t['event_ts'], self.stats)
         planc = self._plan_c(st)
         X = self._buf('X', R, Fp)
         ops.gather_features(planc, row_pos, row_item, R, L, n_cand, t['event_ts'], t['max_ts'], X)
@@ -372,7 +404,7 @@ class NarEngine:
         if keep:
             # X and H1 are overwritten in place by the backward pass: keep copies for the parity tests
             self.last = dict(X=X.clone(), H1=H1.clone(), E=E, HO=HO, F1=F1, PR=PR, logits=logits, row_pos=row_pos,
-                             row_item=row_item, stats=self.stats.clone(), neg=neg_local)
+                             row_item=row_item, stats=st['stats'].clone(), neg=neg_local)
         if not train:
             return out
         # =================================================================== backward
@@ -427,6 +459,35 @@ class NarEngine:
         self.global_step += 1
         ops.adam_tf(self.params, self.grads, self.adam_m, self.adam_v, self.layout.total, self.layout.reg_end,
                     self.reg, self.lr, self.global_step, params_lo=self.params_lo)
+
+    # ---- pipelined interface: submit step n, overlap staging + prepare of step n+1 (side stream), then result(n)
+    def side_stream(self) -> torch.cuda.Stream:
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+        return self._side
+
+    def stage_ahead(self, features, labels, buffer, pop_norm, slot: str) -> dict:
+        """H2D copy + sampler / row lists / statistics of the NEXT step on the side stream."""
+        side = self.side_stream()
+        st = self.stage(features, labels, buffer, pop_norm, slot=slot, stream=side)
+        return self.prepare(st, self.global_step + 1, stream=side)
+
+    def submit(self, st: dict, keep: bool = False) -> dict:
+        self.grads.zero_()
+        out = self.step(st, train=True, keep=keep)
+        if st['L'] > 0 or self.world > 1:
+            self.apply_gradients()
+        if self.world > 1:
+            torch.distributed.all_reduce(self.loss_dev, group=self.pg)
+        self.loss_host.copy_(self.loss_dev, non_blocking=True)
+        out['stage'] = st
+        return out
+
+    def result(self, out: dict) -> dict:
+        torch.cuda.current_stream().synchronize()
+        out['xe_loss'] = float(self.loss_host[0]); out['reg_loss'] = float(self.loss_host[1])
+        out['total_loss'] = out['xe_loss'] + out['reg_loss']
+        return out
 
     def train_step(self, features, labels, buffer, pop_norm, keep: bool = False, sync: bool = True) -> dict:
         st = self.stage(features, labels, buffer, pop_norm)

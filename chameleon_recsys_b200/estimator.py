@@ -114,32 +114,53 @@ class Estimator:
         return self._spec
 
     def train(self, input_fn, steps: Optional[int] = None, hooks=None):
+        """hook.before_run -> train_op -> hook.after_run per batch (MonitoredTrainingSession), software-pipelined:
+        while the GPU runs step n, the host folds batch n into ClickedItemsState (it depends on the batch's ids only,
+        nar_model.py:1635-1650), fetches batch n+1 (tf.data prefetch(1), datasets.py:142) and stages it - H2D copy,
+        negative sampling, row lists, normalisation statistics - on a side stream; then it reads the loss of step n."""
         it = input_fn()
-        n = 0
-        spec = None
-        while steps is None or n < steps:
+
+        def fetch():
             try:
-                features, labels = it.get_next() if hasattr(it, 'get_next') else next(it)
+                return it.get_next() if hasattr(it, 'get_next') else next(it)
             except (OutOfRangeError, StopIteration):
-                break
-            spec = self._ensure_spec(features, labels)
-            if n == 0:
-                for h in spec.training_chief_hooks:
-                    h.begin()
+                return None
+
+        def feed_of(spec):
             feed = {}
             for h in spec.training_chief_hooks:
                 feed.update(h.before_run(None))
-            out = spec.train_op(features, labels, feed)
+            return feed
+
+        n = 0
+        nxt = fetch() if (steps is None or steps > 0) else None
+        if nxt is None:
+            return self
+        spec = self._ensure_spec(*nxt)
+        eng = spec.model.engine
+        for h in spec.training_chief_hooks:
+            h.begin()
+        feed = feed_of(spec)
+        st_next = eng.stage_ahead(nxt[0], nxt[1], feed['pop_recent_items_buffer'], feed['articles_recent_pop_norm'], 'pipe0')
+        while nxt is not None:
+            features, labels = nxt
+            out = eng.submit(st_next)                               # step n queued on the main stream
             run_values = {'clicked_items': features['item_clicked'], 'clicked_timestamps': features['event_timestamp'],
                           'last_item_label': labels['label_last_item']}
             for h in spec.training_chief_hooks:
-                h.after_run(None, run_values)
+                h.after_run(None, run_values)                        # host state now describes "before step n+1"
+            n += 1
+            nxt = fetch() if (steps is None or n < steps) else None
+            if nxt is not None:
+                feed = feed_of(spec)
+                st_next = eng.stage_ahead(nxt[0], nxt[1], feed['pop_recent_items_buffer'],
+                                          feed['articles_recent_pop_norm'], 'pipe%d' % (n & 1))
+            out = eng.result(out)                                   # D2H loss of step n (sync)
+            spec.model._publish(features, labels, out)
             self.last_loss = out.get('total_loss')
             self.interactions += int(out['stage']['L_global'])
-            n += 1
-        if spec is not None:
-            for h in spec.training_chief_hooks:
-                h.end()
+        for h in spec.training_chief_hooks:
+            h.end()
         return self
 
     @property

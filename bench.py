@@ -244,7 +244,7 @@ def run_ours(args):
         eng.grads.zero_()
         eng.step(st, train=True)
         eng.apply_gradients()
-        if i + 1 < len(staged):
+        if eng.use_side_stream and i + 1 < len(staged):
             eng.prepare(staged[i + 1], eng.global_step + 1, stream=side)
 
     for i in range(args.warmup):

@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -92,6 +93,7 @@ class NarEngine:
         self._sampler_ws = None
         self._planc_static = None
         self._side = None
+        self.use_side_stream = os.environ.get('NAR_SIDE_STREAM') == '1'
         self._views: dict = {}
         self.last: Dict[str, torch.Tensor] = {}
         self.ops = ops
@@ -467,10 +469,15 @@ class NarEngine:
         return self._side
 
     def stage_ahead(self, features, labels, buffer, pop_norm, slot: str) -> dict:
-        """H2D copy + sampler / row lists / statistics of the NEXT step on the side stream."""
-        side = self.side_stream()
-        st = self.stage(features, labels, buffer, pop_norm, slot=slot, stream=side)
-        return self.prepare(st, self.global_step + 1, stream=side)
+        """Stage the NEXT step while the current one runs: the host packs the batch into the slot's pinned buffer and
+        queues the H2D copy behind the running step.  With NAR_SIDE_STREAM=1 the copy and the weight-independent front
+        (sampler, row lists, statistics) go to a side stream instead; measured on B200 that is SLOWER (3.3 vs 2.4 ms
+        per step): the many small side-stream CTAs fragment the SMs the 1-CTA-per-SM GEMMs need, so it is off."""
+        if self.use_side_stream:
+            side = self.side_stream()
+            st = self.stage(features, labels, buffer, pop_norm, slot=slot, stream=side)
+            return self.prepare(st, self.global_step + 1, stream=side)
+        return self.stage(features, labels, buffer, pop_norm, slot=slot)
 
     def submit(self, st: dict, keep: bool = False) -> dict:
         self.grads.zero_()

@@ -305,22 +305,23 @@ class NarEngine:
         K = self.K
         n_cand = K + 1
         R = L + L * n_cand
-        slot = st.get('slot', 'stage')
+        # per-slot result buffers are only needed when this runs ahead of the step that is still executing
+        slot = ('/' + st.get('slot', 'stage')) if stream is not None else ''
         cur = torch.cuda.current_stream()
         run_on = stream if stream is not None else cur
         with torch.cuda.stream(run_on):
             need = ops.sample_negatives_workspace(Bg, T + 1, self.buf_len, K)
             if self._sampler_ws is None or self._sampler_ws.numel() < need:
                 self._sampler_ws = torch.zeros(need, dtype=torch.uint8, device=self.dev)
-            neg = self._buf('neg/' + slot, Bg * T, K, torch.int64)
+            neg = self._buf('neg' + slot, Bg * T, K, torch.int64)
             if B < Bg:
                 neg.zero_()
             neg_local = neg.view(-1)[s0 * T * K:(s0 + B) * T * K].view(B, T, K)
             ops.sample_negatives(t['all_items'], s0, B, t['buffer'], K, self.n_from_buffer, self.seed, step_id, neg_local,
                                  self._sampler_ws)
-            stats = self._buf('stats/' + slot, 24, 1).view(-1)
-            row_pos = self._buf('row_pos/' + slot, R, 1, torch.int32).view(-1)
-            row_item = self._buf('row_item/' + slot, R, 1, torch.int64).view(-1)
+            stats = self._buf('stats' + slot, 24, 1).view(-1)
+            row_pos = self._buf('row_pos' + slot, R, 1, torch.int32).view(-1)
+            row_item = self._buf('row_item' + slot, R, 1, torch.int64).view(-1)
             if L > 0:
                 ops.build_rows(t['pos_idx'], L, t['item_clicked'], t['label_next'], neg, K, row_pos, row_item)
                 ops.feature_stats(t['buffer'], self.n_norm, self.created_at, t['pop_norm'], t['max_ts'], self.lb_rec,

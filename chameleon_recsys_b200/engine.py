@@ -93,6 +93,7 @@ class NarEngine:
         self._sampler_ws = None
         self._planc_static = None
         self._side = None
+        self._prep_flip = 0
         self.use_side_stream = os.environ.get('NAR_SIDE_STREAM') == '1'
         self._views: dict = {}
         self.last: Dict[str, torch.Tensor] = {}
@@ -306,7 +307,9 @@ class NarEngine:
         n_cand = K + 1
         R = L + L * n_cand
         # per-slot result buffers are only needed when this runs ahead of the step that is still executing
-        slot = ('/' + st.get('slot', 'stage')) if stream is not None else ''
+        if stream is not None:
+            self._prep_flip ^= 1
+        slot = ('/ahead%d' % self._prep_flip) if stream is not None else ''
         cur = torch.cuda.current_stream()
         run_on = stream if stream is not None else cur
         with torch.cuda.stream(run_on):

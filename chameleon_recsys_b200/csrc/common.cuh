@@ -21,7 +21,12 @@ struct nar_ctx {
   int device;
   int sm_count;
   void* encode_tiled;   // cuTensorMapEncodeTiled entry point
+  // feature gather: device table of per-column descriptors, rebuilt only when the static part of the plan changes
+  void* gather_desc;            // device, NAR_GATHER_DESC_BYTES
+  void* gather_key;             // host copy of the static plan fields the table was built from (nar_feature_plan*)
+  int gather_key_valid;
 };
+#define NAR_GATHER_DESC_BYTES (2 * 512 * 16 + 64)
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

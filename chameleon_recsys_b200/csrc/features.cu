@@ -5,6 +5,8 @@
 // Reference: nar_model.py:921-994 get_item_features, :730-773 get_features, :887-907
 // scale_center_features, :996-1039 normalisation, :1055-1089 recency, :1134-1193 novelty.
 #include "common.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 namespace nar {
 namespace feat {
@@ -62,112 +64,227 @@ __device__ __forceinline__ float seg_value(const nar_feature_plan& P, const nar_
 }
 
 // ------------------------------------------------------------------ forward gather
-// One warp per output row.  Design for HBM speed:
-//  * the per-CTA copy of the column map / segment table lives in shared memory (divergent lookups in the
-//    constant bank would serialise 32x);
-//  * phase A: every scalar the row needs (context ids / floats at its position, metadata of its item,
-//    created_at, pop_norm) is fetched by ONE lane each, all independent -> one memory round trip, then
-//    handed to the lanes that need it with warp shuffles (no dependent load chains per column);
-//  * phase B: the wide table rows (ACR, item embedding) move as 128-bit loads / streaming 128-bit stores;
-//  * phase C: narrow columns, one lane per column.
+// ONE launch, two kinds of CTA, no shared memory, no prologue (a plain row gather of the same bytes runs at HBM
+// speed because thousands of short independent warps are in flight - this kernel keeps that shape):
+//  * "wide" CTAs: one warp per output row moves the wide table rows (ACR, item embedding): ids -> 128-bit
+//    loads -> fma with gamma / beta -> 128-bit streaming stores.  That is ~87 % of the bytes.
+//  * "narrow" CTAs: one warp per (chunk of 8 rows, group of 32 columns) writes the narrow columns (one-hot, small
+//    embeddings, numerics, recency, novelty, padding), one lane per column.  Branch-free: the per-column descriptors (source lane,
+//    kind, table offset / one-hot index, cardinality, stride) come from a device table owned by the context
+//    (rebuilt by a one-CTA kernel only when the static part of the plan changes) and live in registers across
+//    the rows; the scalars a row needs (context ids / floats at its position, metadata of its item) are
+//    fetched by ONE lane each - for all 8 rows back to back, one memory round trip per chunk - finished to a
+//    32-bit word and handed to the column lanes with shuffles; lanes 0-7 / 8-15 compute the normalised recency /
+//    novelty of the 8 rows in one instruction stream.
+//  History (profiles/gather_features_r1*.txt): v1 was bound by the serial instruction stream of each warp
+//  (~1200 instructions per row: per-column switch statements, IEEE divisions + logf + a 64-bit modulo executed by
+//  one lane while 31 idled); splitting showed the narrow columns - 13 % of the bytes - took 2/3 of the time.
 constexpr int GATHER_WARPS = 8;
-constexpr int LANE_CTX_INT = 0, LANE_CTX_FLOAT = 12, LANE_META = 20, LANE_CREATED = 28, LANE_POP = 29;
+constexpr int GATHER_CHUNK = 8;
+constexpr int GATHER_MAX_NARROW = 512;
+constexpr int GATHER_MAX_TAIL = 8;
+constexpr int LANE_CTX_INT = 0, LANE_CTX_FLOAT = 12, LANE_META = 20, LANE_RECENCY = 28, LANE_NOVELTY = 29;
+enum { CK_ZERO = 0, CK_OHE = 1, CK_VALUE = 2, CK_EMBED = 3, CK_PAD = 4, CK_NONE = 0xff };
+enum { SM_NONE = 0, SM_ID_AT_POS = 1, SM_FLOAT_AT_POS = 2, SM_ID_AT_ITEM = 3, SM_NUM_AT_ITEM = 4 };
 
-struct SegS { int kind, col, card, src, ld; const float* table; };
+// device table: d[i] = {col | kind << 16 | src_lane << 24, a, card - 1, ld}; a = one-hot index (CK_OHE) or the
+// offset in floats of table[0][j] from GatherArgs::ebase (CK_EMBED)
+struct GatherDesc {
+  int4 d[GATHER_MAX_NARROW];
+  int n_narrow;
+  int pad_[15];
+};
+static_assert(sizeof(GatherDesc) <= NAR_GATHER_DESC_BYTES, "context scratch too small");
 
-__global__ void __launch_bounds__(GATHER_WARPS * 32)
-gather_features_kernel(const __grid_constant__ nar_feature_plan P, int n_ctx_int, int n_ctx_float, int n_meta,
-                       const int32_t* __restrict__ row_pos,
-                       const int64_t* __restrict__ row_item, int64_t n_rows, int64_t n_input, int64_t n_cand,
+struct GatherArgs {
+  const void* src[32];            // scalar source of lane l (phase A), or NULL
+  unsigned char mode[32];         // SM_*
+  const float* wtab[2];           // wide segments (ACR, item embedding): 16-byte aligned body
+  int wcol[2], wld[2], wnvec[2];
+  int ntail;                      // columns of the wide segments that cannot move as 128-bit vectors
+  short tail_col[GATHER_MAX_TAIL]; unsigned char tail_seg[GATHER_MAX_TAIL]; short tail_j[GATHER_MAX_TAIL];
+  const float* ebase;             // lowest address of the small embedding tables
+  const float* gamma; const float* beta; const float* stats;
+  const int64_t* created_at_ts; const float* pop_norm;
+  float log_base_recency, log_base_novelty;
+  int row_ld, n_narrow_blocks, period, n_col_groups;   // n_col_groups = ceil(narrow columns / 32)
+};
+
+__global__ void __launch_bounds__(128)
+gather_setup_kernel(const __grid_constant__ nar_feature_plan P, int n_narrow_plain, const float* ebase,
+                    GatherDesc* __restrict__ D) {
+  const int tid = threadIdx.x;
+  if (tid == 0) D->n_narrow = n_narrow_plain;
+  for (int i = tid; i < n_narrow_plain; i += blockDim.x) {
+    int c = i, q = 0;
+    while (q < P.n_narrow - 1 && c >= P.narrow_end[q] - P.narrow_begin[q]) { c -= P.narrow_end[q] - P.narrow_begin[q]; ++q; }
+    c += P.narrow_begin[q];
+    const int si = P.col_seg[c];
+    int kind = CK_PAD, src_lane = 0, a = 0, cm1 = 0, ld = 0;      // padding columns are written as 0
+    if (si != 255) {
+      kind = CK_ZERO;
+      const nar_segment& g = P.seg[si];
+      const int j = c - g.col;
+      switch (g.kind) {
+        case NAR_SEG_CTX_OHE: kind = CK_OHE; src_lane = LANE_CTX_INT + g.src; a = j; break;
+        case NAR_SEG_META_OHE: kind = CK_OHE; src_lane = LANE_META + g.src; a = j; break;
+        case NAR_SEG_CTX_EMBED: kind = CK_EMBED; src_lane = LANE_CTX_INT + g.src; a = (int)(g.table + j - ebase); cm1 = g.card - 1; ld = g.ld; break;
+        case NAR_SEG_META_EMBED: kind = CK_EMBED; src_lane = LANE_META + g.src; a = (int)(g.table + j - ebase); cm1 = g.card - 1; ld = g.ld; break;
+        case NAR_SEG_CTX_NUM: kind = CK_VALUE; src_lane = LANE_CTX_FLOAT + g.src; break;
+        case NAR_SEG_META_NUM: kind = CK_VALUE; src_lane = LANE_META + g.src; break;
+        case NAR_SEG_RECENCY: kind = CK_VALUE; src_lane = LANE_RECENCY; break;
+        case NAR_SEG_NOVELTY: kind = CK_VALUE; src_lane = LANE_NOVELTY; break;
+        default: break;   // CTX_ZERO: raw 0 -> beta
+      }
+    }
+    D->d[i] = make_int4(c | (kind << 16) | (src_lane << 24), a, cm1, ld);
+  }
+}
+
+__device__ __forceinline__ int clamp_id32(long long v) {
+  return v < -1 ? -1 : (v > 0x7fffffffLL ? 0x7fffffff : (int)v);
+}
+__device__ __forceinline__ void ld_b64(const void* p, unsigned& lo, unsigned& hi) {
+  asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "l"(p));
+}
+__device__ __forceinline__ void ld_b32(const void* p, unsigned& lo) {
+  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(lo) : "l"(p));
+}
+
+// raw (un-scaled) value of a narrow column, branch-free: z / a / cm1 / ld from the descriptor, val = the
+// scalar of the column's source lane
+__device__ __forceinline__ float narrow_raw(int z, int a, int cm1, int ld, const float* __restrict__ ebase, int val) {
+  const int kind = (z >> 16) & 0xff;
+  const int idx = max(0, min(val, cm1));
+  float re = 0.f;
+  if (kind == CK_EMBED) re = __ldg(ebase + (a + idx * ld));
+  const float r1 = (kind == CK_OHE && val == a) ? 1.f : re;
+  return kind == CK_VALUE ? __int_as_float(val) : r1;
+}
+
+template <int WU>                                  // 128-bit vectors of wide table data per lane and row
+__global__ void __launch_bounds__(GATHER_WARPS * 32, 5)
+gather_features_kernel(const __grid_constant__ GatherArgs A, const GatherDesc* __restrict__ D,
+                       const int32_t* __restrict__ row_pos, const int64_t* __restrict__ row_item,
+                       int n_rows, int n_input, int n_cand,
                        const int64_t* __restrict__ event_ts, const int64_t* __restrict__ max_ts,
                        float* __restrict__ out) {
-  __shared__ uint8_t s_colseg[NAR_MAX_COLS];
-  __shared__ SegS s_seg[NAR_MAX_SEGMENTS];
-  for (int i = threadIdx.x; i < P.row_ld; i += blockDim.x) s_colseg[i] = P.col_seg[i];
-  if (threadIdx.x < P.n_segments) {
-    const nar_segment& g = P.seg[threadIdx.x];
-    s_seg[threadIdx.x] = SegS{g.kind, g.col, g.card, g.src, g.ld, g.table};
-  }
-  __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int64_t r = (int64_t)blockIdx.x * GATHER_WARPS + (threadIdx.x >> 5);
-  if (r >= n_rows) return;
-  const int64_t pos = row_pos[r];
-  const int64_t item = row_item[r];
-  // ---- phase A: scalars, one lane each
-  long long mine = 0;
-  if (lane < LANE_CTX_FLOAT) { if (lane < n_ctx_int) mine = P.ctx_int[lane][pos]; }
-  else if (lane < LANE_META) { if (lane - LANE_CTX_FLOAT < n_ctx_float) mine = (long long)__float_as_int(P.ctx_float[lane - LANE_CTX_FLOAT][pos]); }
-  else if (lane < LANE_CREATED) { if (lane - LANE_META < n_meta) mine = P.meta[lane - LANE_META][item]; }
-  else if (lane == LANE_CREATED) mine = P.created_at_ts[item];
-  else if (lane == LANE_POP) mine = (long long)__float_as_int(P.pop_norm[item]);
-  const int64_t ts_ref = (r < n_input) ? event_ts[pos] : max_ts[0];
-  const float* st = P.stats + 8 * row_group(r, n_input, n_cand);
-  float* orow = out + r * (int64_t)P.row_ld;
-  // ---- phase B: wide table rows
-  for (int s = 0; s < P.n_segments; ++s) {
-    const SegS sg = s_seg[s];
-    if (sg.kind != NAR_SEG_ACR && sg.kind != NAR_SEG_ITEM_EMB) continue;
-    const int width = P.seg[s].width;
-    const float* src = sg.table + item * (int64_t)sg.ld;
-    const bool vec = ((sg.col & 3) == 0) && ((sg.ld & 3) == 0) && ((P.row_ld & 3) == 0);
-    int j0 = 0;
-    if (vec) {
-      const int nv = width >> 2;
-      const float4* s4 = reinterpret_cast<const float4*>(src);
-      const float4* g4 = reinterpret_cast<const float4*>(P.gamma + sg.col);
-      const float4* b4 = reinterpret_cast<const float4*>(P.beta + sg.col);
-      float4* o4 = reinterpret_cast<float4*>(orow + sg.col);
-      for (int j = lane; j < nv; j += 32) {
-        float4 v = __ldg(s4 + j);
-        const float4 g = __ldg(g4 + j), b = __ldg(b4 + j);
-        v.x = v.x * g.x + b.x; v.y = v.y * g.y + b.y; v.z = v.z * g.z + b.z; v.w = v.w * g.w + b.w;
-        __stcs(o4 + j, v);                          // streaming store: the row is consumed once by the GEMM's TMA
-      }
-      j0 = nv << 2;
+  // narrow and wide CTAs are interleaved in launch order (period P): the narrow ones are latency bound, the wide
+  // ones HBM bound, so they should be resident together
+  const int b = (int)blockIdx.x, P = A.period, nbP = A.n_narrow_blocks * P;
+  const bool is_narrow = b < nbP && (b % P) == 0;
+  if (!is_narrow) {
+    // ================================================================ wide CTA: one warp per row
+    const int wblock = b < nbP ? b - b / P - 1 : b - A.n_narrow_blocks;
+    const int r = wblock * GATHER_WARPS + (threadIdx.x >> 5);
+    if (r >= n_rows) return;
+    const long long item = row_item[r];
+    const int nv0 = A.wnvec[0], nvt = nv0 + A.wnvec[1];
+    float* orowf = out + (int64_t)r * A.row_ld;
+    float4* orow = reinterpret_cast<float4*>(orowf);
+    const float* r0 = A.wtab[0] + item * (int64_t)A.wld[0];
+    const float* r1 = A.wtab[1] + item * (int64_t)A.wld[1];
+    const float4* t0 = reinterpret_cast<const float4*>(r0);
+    const float4* t1 = reinterpret_cast<const float4*>(r1) - nv0;
+    const int c0 = A.wcol[0] >> 2, c1 = (A.wcol[1] >> 2) - nv0;
+    float4 wv[WU];
+#pragma unroll
+    for (int u = 0; u < WU; ++u) {
+      const int v = u * 32 + lane;
+      if (v < nvt) wv[u] = __ldg((v >= nv0 ? t1 : t0) + v);
     }
-    for (int j = j0 + lane; j < width; j += 32)
-      orow[sg.col + j] = __ldg(src + j) * P.gamma[sg.col + j] + P.beta[sg.col + j];
+    float tv = 0.f;
+    if (lane < A.ntail) tv = __ldg((A.tail_seg[lane] ? r1 : r0) + A.tail_j[lane]);
+#pragma unroll
+    for (int u = 0; u < WU; ++u) {
+      const int v = u * 32 + lane;
+      if (v < nvt) {
+        const int c4 = (v >= nv0 ? c1 : c0) + v;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(A.gamma) + c4), b = __ldg(reinterpret_cast<const float4*>(A.beta) + c4);
+        float4 x = wv[u];
+        x.x = x.x * g.x + b.x; x.y = x.y * g.y + b.y; x.z = x.z * g.z + b.z; x.w = x.w * g.w + b.w;
+        __stcs(orow + c4, x);                       // streaming store: the row is consumed once by the GEMM's TMA
+      }
+    }
+    if (lane < A.ntail) { const int c = A.tail_col[lane]; orowf[c] = tv * __ldg(A.gamma + c) + __ldg(A.beta + c); }
+    return;
   }
-  // ---- phase C: narrow columns (one-hot, small embeddings, numerics, recency, novelty, padding)
-  const float ilr = 1.0f / logf(P.log_base_recency), iln = 1.0f / logf(P.log_base_novelty);
-  for (int q = 0; q < P.n_narrow; ++q) {
-    const int begin = P.narrow_begin[q], end = P.narrow_end[q];
-    for (int c0 = begin; c0 < end; c0 += 32) {             // warp-uniform trip count (shuffles inside)
-      const int c = c0 + lane;
-      const bool valid = c < end;
-      const int si = valid ? s_colseg[c] : 255;
-      SegS sg = s_seg[si == 255 ? 0 : si];
-      int src_lane = lane;
-      switch (sg.kind) {
-        case NAR_SEG_CTX_OHE: case NAR_SEG_CTX_EMBED: src_lane = LANE_CTX_INT + sg.src; break;
-        case NAR_SEG_CTX_NUM: src_lane = LANE_CTX_FLOAT + sg.src; break;
-        case NAR_SEG_META_OHE: case NAR_SEG_META_EMBED: case NAR_SEG_META_NUM: src_lane = LANE_META + sg.src; break;
-        case NAR_SEG_RECENCY: src_lane = LANE_CREATED; break;
-        case NAR_SEG_NOVELTY: src_lane = LANE_POP; break;
-        default: break;
-      }
-      const long long val = __shfl_sync(0xffffffffu, mine, src_lane);
-      if (!valid) continue;
-      float v = 0.f;
-      if (si != 255) {
-        const int j = c - sg.col;
-        float raw = 0.f;
-        switch (sg.kind) {
-          case NAR_SEG_CTX_OHE: case NAR_SEG_META_OHE: raw = (val == (long long)j) ? 1.f : 0.f; break;
-          case NAR_SEG_CTX_EMBED: case NAR_SEG_META_EMBED: {
-            const long long id = val < 0 ? 0 : (val >= sg.card ? sg.card - 1 : val);
-            raw = __ldg(sg.table + id * sg.ld + j);
-          } break;
-          case NAR_SEG_CTX_NUM: raw = __int_as_float((int)val); break;
-          case NAR_SEG_META_NUM: raw = (float)val; break;
-          case NAR_SEG_RECENCY: raw = normalize(recency_raw(ts_ref, (int64_t)val, ilr), st); break;
-          case NAR_SEG_NOVELTY: raw = normalize(novelty_raw(__int_as_float((int)val), iln), st + 4); break;
-          default: break;
-        }
-        v = raw * P.gamma[c] + P.beta[c];
-      }
-      orow[c] = v;
+  // ================================================================== narrow CTA: one warp per (chunk of 8 rows, 32 columns)
+  constexpr int CH = GATHER_CHUNK;
+  const int w = (b / P) * GATHER_WARPS + (threadIdx.x >> 5);
+  const int chunk = w / A.n_col_groups, n = w - chunk * A.n_col_groups;
+  const int base = chunk * CH;
+  if (base >= n_rows) return;
+  const int rows_here = min(CH, n_rows - base);
+  // this lane's column: descriptor, gamma, beta
+  const int i = n * 32 + lane;
+  int nd_z = CK_NONE << 16, nd_a = 0, nd_c = 0, nd_l = 0;
+  float nd_g = 0.f, nd_b = 0.f;
+  if (i < D->n_narrow) {
+    const int4 d = __ldg(&D->d[i]);
+    nd_z = d.x; nd_a = d.y; nd_c = d.z; nd_l = d.w;
+    if (((d.x >> 16) & 0xff) != CK_PAD) { nd_g = __ldg(A.gamma + (d.x & 0xffff)); nd_b = __ldg(A.beta + (d.x & 0xffff)); }
+  }
+  const int kind = (nd_z >> 16) & 0xff;
+  const bool uses_src = kind == CK_OHE || kind == CK_VALUE || kind == CK_EMBED;
+  // which scalar sources do the 32 columns of this warp need?
+  const unsigned need = __reduce_or_sync(0xffffffffu, uses_src ? (1u << ((unsigned)nd_z >> 24)) : 0u);
+  const int my_mode = ((need >> lane) & 1u) ? A.mode[lane] : SM_NONE;
+  const char* my_src = static_cast<const char*>(A.src[lane]);
+  int c_pos = 0; long long c_item = 0; float c_norm = 0.f;
+  if ((lane & 7) < rows_here) {
+    const int rr = base + (lane & 7);
+    c_pos = row_pos[rr]; c_item = row_item[rr];
+  }
+  // ---- the scalars of all rows, one lane per source, all loads in flight together
+  unsigned lo[CH], hi[CH];
+#pragma unroll
+  for (int k = 0; k < CH; ++k) {
+    const int pos = __shfl_sync(0xffffffffu, c_pos, k);
+    const long long item = __shfl_sync(0xffffffffu, c_item, k);
+    lo[k] = 0; hi[k] = 0;
+    if (k < rows_here) {
+      if (my_mode == SM_FLOAT_AT_POS) ld_b32(my_src + 4 * (int64_t)pos, lo[k]);
+      else if (my_mode == SM_ID_AT_POS) ld_b64(my_src + 8 * (int64_t)pos, lo[k], hi[k]);
+      else if (my_mode >= SM_ID_AT_ITEM) ld_b64(my_src + 8 * item, lo[k], hi[k]);
+    }
+  }
+  // ---- normalised recency (lanes 0-7) / novelty (lanes 8-15) of the chunk's rows, if a column here needs them
+  const int role = lane >> 3;
+  if ((lane & 7) < rows_here && role < 2 && ((need >> (LANE_RECENCY + role)) & 1u)) {
+    const int rr = base + (lane & 7);
+    float x, scale;
+    if (role == 0) {
+      const int64_t ts_ref = (rr < n_input) ? event_ts[c_pos] : max_ts[0];
+      // nar_model.py:1055-1060: int64 -> float32 BEFORE the subtraction; _rn intrinsics, see recency_raw()
+      const float days = fmaxf(__fdiv_rn(__fsub_rn(__ll2float_rn(ts_ref), __ll2float_rn(A.created_at_ts[c_item])), MS_PER_DAY), 0.f);
+      x = __fadd_rn(days, 1.0f);
+      scale = 1.0f / logf(A.log_base_recency);
+    } else {
+      x = A.pop_norm[c_item];
+      scale = -(1.0f / logf(A.log_base_novelty));
+    }
+    const float raw = __fmul_rn(logf(x), scale);               // == recency_raw / novelty_raw bit for bit
+    const int g = rr < n_input ? 0 : (n_cand <= 0 ? 2 : (((unsigned)(rr - n_input) % (unsigned)n_cand) == 0 ? 1 : 2));
+    c_norm = normalize(raw, A.stats + 8 * g + 4 * role);
+  }
+  const int src_lane = (unsigned)nd_z >> 24;
+  float* ocol = out + (int64_t)base * A.row_ld + (nd_z & 0xffff);
+#pragma unroll
+  for (int k = 0; k < CH; ++k) {
+    if (k < rows_here) {
+      const float nrm = __shfl_sync(0xffffffffu, c_norm, (lane == LANE_NOVELTY ? 8 : 0) + k);
+      // finish the scalar (branch-free): int64 -> clamped int32 id / float, one 32-bit word to shuffle
+      const long long a64 = (long long)(((unsigned long long)hi[k] << 32) | lo[k]);
+      const int as_id = clamp_id32(a64);
+      const int as_num = __float_as_int((float)a64);
+      int mine = my_mode == SM_NONE ? __float_as_int(nrm) : as_id;     // lanes LANE_RECENCY / LANE_NOVELTY: SM_NONE
+      mine = my_mode == SM_FLOAT_AT_POS ? (int)lo[k] : mine;
+      mine = my_mode == SM_NUM_AT_ITEM ? as_num : mine;
+      const int val = __shfl_sync(0xffffffffu, mine, src_lane);
+      const float raw = narrow_raw(nd_z, nd_a, nd_c, nd_l, A.ebase, val);
+      if (kind != CK_NONE) ocol[(int64_t)k * A.row_ld] = raw * nd_g + nd_b;
     }
   }
 }
@@ -418,18 +535,89 @@ extern "C" int nar_gather_features(nar_ctx* ctx, const nar_feature_plan* plan, c
   if (!ctx || !plan || !row_pos || !row_item || !out || !max_ts) return NAR_ERR_INVALID;
   if (plan->n_segments > NAR_MAX_SEGMENTS) return NAR_ERR_INVALID;
   if (n_rows <= 0) return NAR_OK;
-  const unsigned grid = (unsigned)((n_rows + nar::feat::GATHER_WARPS - 1) / nar::feat::GATHER_WARPS);
+  if (!ctx || !ctx->gather_desc) return NAR_ERR_INVALID;
   // lane budget of the scalar prefetch (phase A): <= 12 context ids, <= 8 context floats, <= 8 metadata arrays
-  int n_ci = 0, n_cf = 0, n_me = 0;
+  int n_ci = 0, n_cf = 0, n_me = 0, n_wide = 0, n_narrow_cols = 0, n_tail = 0, n_vec = 0;
+  unsigned meta_num_mask = 0;
+  nar::feat::GatherArgs A;
+  memset(&A, 0, sizeof(A));
+  const float* e_lo = nullptr; const float* e_hi = nullptr;     // address range of the small embedding tables
   for (int i = 0; i < plan->n_segments; ++i) {
     const nar_segment& g = plan->seg[i];
     if (g.kind == NAR_SEG_CTX_OHE || g.kind == NAR_SEG_CTX_EMBED) n_ci = g.src + 1 > n_ci ? g.src + 1 : n_ci;
     if (g.kind == NAR_SEG_CTX_NUM) n_cf = g.src + 1 > n_cf ? g.src + 1 : n_cf;
     if (g.kind == NAR_SEG_META_OHE || g.kind == NAR_SEG_META_EMBED || g.kind == NAR_SEG_META_NUM) n_me = g.src + 1 > n_me ? g.src + 1 : n_me;
+    if (g.kind == NAR_SEG_META_NUM && g.src < 32) meta_num_mask |= 1u << g.src;
+    if (g.kind == NAR_SEG_ACR || g.kind == NAR_SEG_ITEM_EMB) {
+      const bool vec = ((g.col & 3) == 0) && ((g.ld & 3) == 0) && ((plan->row_ld & 3) == 0);
+      if (n_wide < 2) {
+        A.wtab[n_wide] = g.table; A.wcol[n_wide] = g.col; A.wld[n_wide] = g.ld; A.wnvec[n_wide] = vec ? (g.width >> 2) : 0;
+        for (int j = vec ? (g.width & ~3) : 0; j < g.width; ++j, ++n_tail)
+          if (n_tail < nar::feat::GATHER_MAX_TAIL) { A.tail_col[n_tail] = (short)(g.col + j); A.tail_seg[n_tail] = (unsigned char)n_wide; A.tail_j[n_tail] = (short)j; }
+      }
+      ++n_wide;
+      n_vec += vec ? (g.width >> 2) : 0;
+    }
+    if (g.kind == NAR_SEG_CTX_EMBED || g.kind == NAR_SEG_META_EMBED) {
+      if (!e_lo || g.table < e_lo) e_lo = g.table;
+      const float* end = g.table + (int64_t)g.card * g.ld;
+      if (!e_hi || end > e_hi) e_hi = end;
+    }
   }
-  if (n_ci > 12 || n_cf > 8 || n_me > 8 || plan->row_ld > NAR_MAX_COLS) return NAR_ERR_UNSUPPORTED;
-  nar::feat::gather_features_kernel<<<grid, nar::feat::GATHER_WARPS * 32, 0, as_stream(stream)>>>(
-      *plan, n_ci, n_cf, n_me, row_pos, row_item, n_rows, n_input, n_cand, event_timestamp, max_ts, out);
+  for (int q = 0; q < plan->n_narrow; ++q) n_narrow_cols += plan->narrow_end[q] - plan->narrow_begin[q];
+  if (n_ci > 12 || n_cf > 8 || n_me > 8 || n_wide > 2 || plan->row_ld > NAR_MAX_COLS || plan->row_ld > 0xffff ||
+      n_narrow_cols > nar::feat::GATHER_MAX_NARROW || n_tail > nar::feat::GATHER_MAX_TAIL || n_vec > 4 * 32 ||
+      n_rows > 0x7fffffffLL / 2 || (e_hi - e_lo) > 0x7fffffffLL ||     // table offsets are 32-bit (one flat parameter buffer)
+      (reinterpret_cast<uintptr_t>(plan->gamma) & 15) || (reinterpret_cast<uintptr_t>(plan->beta) & 15) ||
+      (reinterpret_cast<uintptr_t>(out) & 15)) return NAR_ERR_UNSUPPORTED;
+  // descriptor table: rebuilt only when the static part of the plan changed (calls sharing a context are stream-ordered)
+  {
+    nar_feature_plan* key = static_cast<nar_feature_plan*>(ctx->gather_key);
+    bool same = ctx->gather_key_valid && key->n_segments == plan->n_segments && key->row_ld == plan->row_ld &&
+                key->n_narrow == plan->n_narrow &&
+                memcmp(key->seg, plan->seg, sizeof(nar_segment) * plan->n_segments) == 0 &&
+                memcmp(key->narrow_begin, plan->narrow_begin, sizeof(plan->narrow_begin)) == 0 &&
+                memcmp(key->narrow_end, plan->narrow_end, sizeof(plan->narrow_end)) == 0 &&
+                memcmp(key->col_seg, plan->col_seg, plan->row_ld) == 0;
+    if (!same) {
+      nar::feat::gather_setup_kernel<<<1, 128, 0, as_stream(stream)>>>(*plan, n_narrow_cols, e_lo,
+                                                                       static_cast<nar::feat::GatherDesc*>(ctx->gather_desc));
+      NAR_LAUNCH_CHECK();
+      *key = *plan;
+      ctx->gather_key_valid = 1;
+    }
+  }
+  for (int l = 0; l < 32; ++l) {
+    const void* p = nullptr; int mode = nar::feat::SM_NONE;
+    if (l < nar::feat::LANE_CTX_FLOAT) { if (l < n_ci) { p = plan->ctx_int[l]; mode = nar::feat::SM_ID_AT_POS; } }
+    else if (l < nar::feat::LANE_META) { if (l - nar::feat::LANE_CTX_FLOAT < n_cf) { p = plan->ctx_float[l - nar::feat::LANE_CTX_FLOAT]; mode = nar::feat::SM_FLOAT_AT_POS; } }
+    else if (l < nar::feat::LANE_RECENCY) {
+      const int m = l - nar::feat::LANE_META;
+      if (m < n_me) { p = plan->meta[m]; mode = ((meta_num_mask >> m) & 1u) ? nar::feat::SM_NUM_AT_ITEM : nar::feat::SM_ID_AT_ITEM; }
+    }
+    A.src[l] = p; A.mode[l] = (unsigned char)(p ? mode : nar::feat::SM_NONE);
+  }
+  A.gamma = plan->gamma; A.beta = plan->beta; A.stats = plan->stats;
+  A.created_at_ts = plan->created_at_ts; A.pop_norm = plan->pop_norm;
+  A.log_base_recency = plan->log_base_recency; A.log_base_novelty = plan->log_base_novelty;
+  A.row_ld = plan->row_ld;
+  A.ebase = e_lo; A.ntail = n_tail;
+  const nar::feat::GatherDesc* D = static_cast<const nar::feat::GatherDesc*>(ctx->gather_desc);
+  // narrow CTAs first (longer running): one warp per (chunk of 8 rows, 32 columns); then one wide CTA per 8 rows
+  const int64_t n_chunks = (n_rows + nar::feat::GATHER_CHUNK - 1) / nar::feat::GATHER_CHUNK;
+  A.n_col_groups = (n_narrow_cols + 31) / 32;
+  const int64_t nb = (n_chunks * A.n_col_groups + nar::feat::GATHER_WARPS - 1) / nar::feat::GATHER_WARPS;
+  A.n_narrow_blocks = (int)nb;
+  const int64_t wb = (n_vec > 0 || n_tail > 0) ? (n_rows + nar::feat::GATHER_WARPS - 1) / nar::feat::GATHER_WARPS : 0;
+  const unsigned grid = (unsigned)(nb + wb);
+  if (grid == 0) return NAR_OK;
+  A.period = nb > 0 ? (int)((nb + wb) / nb) : 1;
+  const int wu = (n_vec + 31) / 32;
+#define NAR_GATHER_LAUNCH(WU)                                                                                     \
+  nar::feat::gather_features_kernel<WU><<<grid, nar::feat::GATHER_WARPS * 32, 0, as_stream(stream)>>>(            \
+      A, D, row_pos, row_item, (int)n_rows, (int)n_input, (int)n_cand, event_timestamp, max_ts, out)
+  if (wu <= 1) NAR_GATHER_LAUNCH(1); else if (wu == 2) NAR_GATHER_LAUNCH(2); else if (wu == 3) NAR_GATHER_LAUNCH(3); else NAR_GATHER_LAUNCH(4);
+#undef NAR_GATHER_LAUNCH
   NAR_LAUNCH_CHECK();
   return NAR_OK;
 }

@@ -1,6 +1,7 @@
 // Context + small HBM-bound helpers: TF-flavoured Adam, column sums (bias grads), l2 loss,
 // transpose (Wh^T for BPTT), activation backward.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace nar {
 namespace misc {
@@ -124,11 +125,15 @@ extern "C" int nar_ctx_create(int device, nar_ctx** out) {
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   c->encode_tiled = fn;
+  c->gather_desc = nullptr; c->gather_key = nullptr; c->gather_key_valid = 0;
+  if (cudaMalloc(&c->gather_desc, NAR_GATHER_DESC_BYTES) != cudaSuccess) { delete c; return NAR_ERR_NO_DEVICE; }
+  c->gather_key = malloc(sizeof(nar_feature_plan));
   *out = c;
   return NAR_OK;
 }
 
 extern "C" int nar_ctx_destroy(nar_ctx* ctx) {
+  if (ctx) { cudaFree(ctx->gather_desc); free(ctx->gather_key); }
   delete ctx;
   return NAR_OK;
 }

@@ -142,11 +142,14 @@ class NarEngine:
         ops.tf32_lo(self.params, self.layout.total, self.params_lo)
 
     # ------------------------------------------------------------------ buffers
-    def _buf(self, name: str, rows: int, cols: int, dtype=torch.float32) -> torch.Tensor:
+    def _buf(self, name: str, rows: int, cols: int, dtype=torch.float32, cap_rows: int = 0) -> torch.Tensor:
+        """Named device buffer.  ``cap_rows`` = the most rows this buffer can ever need (every position of every session
+        valid): allocated once at that size - a (re)allocation inside the training loop is a device-wide sync, and
+        with 180 GB of HBM the worst case of the reference configurations (a few GB) is cheap."""
         need = max(1, rows) * cols
         t = self._bufs.get(name)
         if t is None or t.numel() < need or t.dtype != dtype:
-            cap = int(need * 1.25) + 1024
+            cap = max(int(need * 1.25) + 1024, max(1, cap_rows) * cols)
             t = torch.empty(cap, device=self.dev, dtype=dtype)
             self._bufs[name] = t
         return t[:max(1, rows) * cols].view(max(1, rows), cols)
@@ -189,12 +192,13 @@ class NarEngine:
             offs[name] = (off, arr.size, dt, arr.shape)
             off += arr.size * np.dtype(dt).itemsize
         total = round_up(off, 16)
-        pin = self._pin(slot, total)
+        worst = total + 4 * (per * T - pos_idx.size) + 64       # pos_idx is the only part whose size varies step to step
+        pin = self._pin(slot, worst)
         pin_np = pin.numpy()
         for name, arr, dt in parts:
             o, nel, _, _ = offs[name]
             pin_np[o:o + nel * np.dtype(dt).itemsize].view(dt)[:] = arr.reshape(-1)
-        dev = self._buf(slot, total, 1, torch.uint8).view(-1)
+        dev = self._buf(slot, total, 1, torch.uint8, cap_rows=worst).view(-1)
         with torch.cuda.stream(stream if stream is not None else torch.cuda.current_stream()):
             dev[:total].copy_(pin[:total], non_blocking=True)
         tmap = {np.int64: torch.int64, np.float32: torch.float32, np.int32: torch.int32}
@@ -306,6 +310,7 @@ class NarEngine:
         K = self.K
         n_cand = K + 1
         R = L + L * n_cand
+        Rmax = B * T * (n_cand + 1)                       # every position of every local session valid
         # per-slot result buffers are only needed when this runs ahead of the step that is still executing
         if stream is not None:
             self._prep_flip ^= 1
@@ -323,8 +328,8 @@ class NarEngine:
             ops.sample_negatives(t['all_items'], s0, B, t['buffer'], K, self.n_from_buffer, self.seed, step_id, neg_local,
                                  self._sampler_ws)
             stats = self._buf('stats' + slot, 24, 1).view(-1)
-            row_pos = self._buf('row_pos' + slot, R, 1, torch.int32).view(-1)
-            row_item = self._buf('row_item' + slot, R, 1, torch.int64).view(-1)
+            row_pos = self._buf('row_pos' + slot, R, 1, torch.int32, cap_rows=Rmax).view(-1)
+            row_item = self._buf('row_item' + slot, R, 1, torch.int64, cap_rows=Rmax).view(-1)
             if L > 0:
                 ops.build_rows(t['pos_idx'], L, t['item_clicked'], t['label_next'], neg, K, row_pos, row_item)
                 ops.feature_stats(t['buffer'], self.n_norm, self.created_at, t['pop_norm'], t['max_ts'], self.lb_rec,
@@ -345,6 +350,8 @@ class NarEngine:
         n_cand = K + 1
         Rc = L * n_cand
         R = L + Rc
+        Lmax = B * T                                      # worst case: every position of every local session valid
+        Rcmax, Rmax = Lmax * n_cand, Lmax * (n_cand + 1)
         inv_count = 1.0 / max(1, st['L_global'])
         step_id = self.global_step + 1
         self.loss_dev.zero_()
@@ -360,41 +367,41 @@ class NarEngine:
             out.update(loss=self.loss_dev, logits=None)
             return out
         planc = self._plan_c(st)
-        X = self._buf('X', R, Fp)
+        X = self._buf('X', R, Fp, cap_rows=Rmax)
         ops.gather_features(planc, row_pos, row_item, R, L, n_cand, t['event_ts'], t['max_ts'], X)
         # ---- CAR (nar_model.py:374-405)
-        H1 = self._buf('H1', R, C_)
-        E = self._buf('E', R, C_)
+        H1 = self._buf('H1', R, C_, cap_rows=Rmax)
+        E = self._buf('E', R, C_, cap_rows=Rmax)
         self._fwd(X, 'W1', 'b1', H1, R, ACT_LEAKY)
         self._fwd(H1, 'W2', 'b2', E, R, ACT_TANH)
         # ---- RNN (nar_model.py:408, :1308-1342)
         rnn_in = E
         HO, GT, CD, GX = [], [], [], []
         for i in range(self.layers):
-            gx = self._buf('GX%d' % i, L, 2 * Hp)
-            ho = self._buf('HO%d' % i, L, Hp); gt = self._buf('GT%d' % i, L, Hp); cd = self._buf('CD%d' % i, L, Hp)
+            gx = self._buf('GX%d' % i, L, 2 * Hp, cap_rows=Lmax)
+            ho = self._buf('HO%d' % i, L, Hp, cap_rows=Lmax); gt = self._buf('GT%d' % i, L, Hp, cap_rows=Lmax); cd = self._buf('CD%d' % i, L, Hp, cap_rows=Lmax)
             self._fwd(rnn_in, 'rnn%d/Wx' % i, 'rnn%d/b' % i, gx, L, ACT_NONE)
             ops.ugrnn_fwd(gx, self.view('rnn%d/Wh' % i), t['sess_off'], B, Hp, ho, gt, cd)
             HO.append(ho); GT.append(gt); CD.append(cd); GX.append(gx)
             rnn_in = ho
         # ---- session representation (nar_model.py:410-438)
-        F1 = self._buf('F1', L, 512)
-        PR = self._buf('PR', L, C_)
+        F1 = self._buf('F1', L, 512, cap_rows=Lmax)
+        PR = self._buf('PR', L, C_, cap_rows=Lmax)
         self._fwd(HO[-1], 'W3', 'b3', F1, L, ACT_LEAKY)
         self._fwd(F1, 'W4', 'b4', PR, L, ACT_TANH)
         # ---- scorer + loss (nar_model.py:444-517, :639-667)
         Ec = E[L:]
-        logits = self._buf('logits', L, n_cand)
-        dE = self._buf('dE', R, C_) if train else None
-        dPR = self._buf('dPR', L, C_) if train else None
+        logits = self._buf('logits', L, n_cand, cap_rows=Lmax)
+        dE = self._buf('dE', R, C_, cap_rows=Rmax) if train else None
+        dPR = self._buf('dPR', L, C_, cap_rows=Lmax) if train else None
         if self.ranking == 'mlp':
-            PD = self._buf('PD', Rc, C_)
-            Z1 = self._buf('Z1', Rc, 128); Z2 = self._buf('Z2', Rc, 64); Z3 = self._buf('Z3', Rc, 32)
+            PD = self._buf('PD', Rc, C_, cap_rows=Rcmax)
+            Z1 = self._buf('Z1', Rc, 128, cap_rows=Rcmax); Z2 = self._buf('Z2', Rc, 64, cap_rows=Rcmax); Z3 = self._buf('Z3', Rc, 32, cap_rows=Rcmax)
             ops.mul_pred(Ec, PR, L, n_cand, C_, PD)
             self._fwd(PD, 'M1', 'c1', Z1, Rc, ACT_LEAKY)
             self._fwd(Z1, 'M2', 'c2', Z2, Rc, ACT_LEAKY)
             self._fwd(Z2, 'M3', 'c3', Z3, Rc, ACT_LEAKY)
-            dZ3 = self._buf('dZ3', Rc, 32) if train else None
+            dZ3 = self._buf('dZ3', Rc, 32, cap_rows=Rcmax) if train else None
             m4 = self.view('M4'); c4 = self.view('c4')
             ops.score_softmax_ce(Z3, 32, 32, m4, m4.stride(0), c4, L, n_cand, 1.0 / self.tau, inv_count, logits,
                                  self.loss_dev[0:1], dZ3, self.view('M4', self.grads) if train else None,
@@ -415,7 +422,7 @@ class NarEngine:
             return out
         # =================================================================== backward
         if self.ranking == 'mlp':
-            dZ2 = self._buf('dZ2', Rc, 64); dZ1 = self._buf('dZ1', Rc, 128)
+            dZ2 = self._buf('dZ2', Rc, 64, cap_rows=Rcmax); dZ1 = self._buf('dZ1', Rc, 128, cap_rows=Rcmax)
             self._wgrad(Z2, dZ3, 'M3', Rc); self._bgrad(dZ3, 'c3', Rc, 32)
             self._dgrad(dZ3, 'M3', dZ2, Rc, dact=ACT_LEAKY, aux=Z2)
             self._wgrad(Z1, dZ2, 'M2', Rc); self._bgrad(dZ2, 'c2', Rc, 64)
@@ -428,16 +435,16 @@ class NarEngine:
         # FC2 / FC1 (nar_model.py:410-426)
         ops.act_bwd(dPR, PR, L * C_, ACT_TANH, dPR)
         self._wgrad(F1, dPR, 'W4', L); self._bgrad(dPR, 'b4', L, C_)
-        dF1 = self._buf('dF1', L, 512)
+        dF1 = self._buf('dF1', L, 512, cap_rows=Lmax)
         self._dgrad(dPR, 'W4', dF1, L, dact=ACT_LEAKY, aux=F1)
         self._wgrad(HO[-1], dF1, 'W3', L); self._bgrad(dF1, 'b3', L, 512)
-        dHO = self._buf('dHO', L, Hp)
+        dHO = self._buf('dHO', L, Hp, cap_rows=Lmax)
         self._dgrad(dF1, 'W3', dHO, L)
         # RNN BPTT
         for i in reversed(range(self.layers)):
             Wh = self.view('rnn%d/Wh' % i)
             ops.transpose(Wh, Hp, 2 * Hp, 2 * Hp, self.WhT[i], Hp)
-            dGX = self._buf('dGX', L, 2 * Hp); HPV = self._buf('HPV', L, Hp)
+            dGX = self._buf('dGX', L, 2 * Hp, cap_rows=Lmax); HPV = self._buf('HPV', L, Hp, cap_rows=Lmax)
             ops.ugrnn_bwd(dHO, HO[i], GT[i], CD[i], self.WhT[i], t['sess_off'], B, Hp, dGX, HPV)
             x_in = E if i == 0 else HO[i - 1]
             self._wgrad(x_in, dGX, 'rnn%d/Wx' % i, L)
@@ -446,7 +453,7 @@ class NarEngine:
             if i == 0:
                 self._dgrad(dGX, 'rnn0/Wx', dE, L, dact=ACT_TANH, aux=E)      # input rows of dE (pre-tanh)
             else:
-                dprev = self._buf('dHO_b', L, Hp)
+                dprev = self._buf('dHO_b', L, Hp, cap_rows=Lmax)
                 self._dgrad(dGX, 'rnn%d/Wx' % i, dprev, L)
                 dHO = dprev
         # CAR (shared weights: inputs + positives + negatives in one GEMM)

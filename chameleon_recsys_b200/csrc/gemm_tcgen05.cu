@@ -26,6 +26,8 @@
 //   MODE 0: single pass.   MODE 1: 3x, both lo tiles produced in-kernel.
 //   MODE 2: 3x, B_lo (weights) read from HBM by TMA (nar_adam_tf maintains it), only A is split in-kernel.
 #include "common.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 namespace nar {
 namespace gemm {
@@ -69,6 +71,8 @@ struct Params {
   int act, dact, accumulate;
   int k_tiles_per_split;
   int n_tiles;                 // blockIdx.x = m_blk * n_tiles + n_blk (N fastest: CTAs sharing an A tile run together)
+  int cluster;                 // 1: launched as clusters of 2 CTAs that own M-tiles 2j / 2j+1 of the SAME N-tile; each CTA
+                               // fetches half of the B tile(s) and TMA-multicasts it into both CTAs' shared memory
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -108,6 +112,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// multicast form: the box lands at the same shared-memory offset in every CTA of `mask`, and signals the mbarrier at
+// the same offset in each of them
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -146,6 +161,10 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {     // arrive on `bar` in every CTA of mask
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -231,6 +250,19 @@ __device__ __forceinline__ void load_operand(uint32_t dst, const CUtensorMap* ma
   }
 }
 
+// cluster form: this CTA (rank r of 2) fetches HALF of the tile and multicasts it to both CTAs.  K-major: `map` has a
+// box of 64*T rows; MN-major: 2*T of the 4*T boxes.
+template <bool MN_MAJOR, int T>
+__device__ __forceinline__ void load_operand_mc(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int mn0, int k_elem, int r) {
+  if (!MN_MAJOR) {
+    tma_load_2d_mc(dst + r * (64 * T * 128), map, bar, k_elem, mn0 + r * 64 * T, (uint16_t)3);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 2 * T; ++i)
+      tma_load_2d_mc(dst + (r * 2 * T + i) * 4096, map, bar, mn0 + (r * 2 * T + i) * 32, k_elem, (uint16_t)3);
+  }
+}
+
 // ---------------------------------------------------------------- kernel
 template <bool A_MN, bool B_MN, int MODE, int TM, int TN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -255,7 +287,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_blk = blockIdx.x % p.n_tiles, m_blk = blockIdx.x / p.n_tiles;
+  // cluster mode: CTAs 2j, 2j+1 (= cluster ranks 0, 1) own M-tiles 2*(j / n_tiles) + rank of N-tile j % n_tiles
+  const int crank = p.cluster ? (int)(blockIdx.x & 1u) : 0;
+  const int n_blk = p.cluster ? (int)((blockIdx.x >> 1) % p.n_tiles) : (int)(blockIdx.x % p.n_tiles);
+  const int m_blk = p.cluster ? (int)((blockIdx.x >> 1) / p.n_tiles) * 2 + crank : (int)(blockIdx.x / p.n_tiles);
   const int k_tiles_total = (int)((p.K + BK - 1) / BK);
   const int kt0 = blockIdx.y * p.k_tiles_per_split;
   const int kt1 = min(kt0 + p.k_tiles_per_split, k_tiles_total);
@@ -269,7 +304,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp_idx == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], ATMEM ? 129 : 1);      // MODE 3: the A tile is released by the 128 split threads, B by the MMA commit
+      // MODE 3: the A tile is released by the 128 split threads, B by the MMA commit; cluster: the peer CTA's MMAs read
+      // the B half this CTA multicasts, so its commit releases the stage too
+      mbar_init(&empty[s], (ATMEM ? 129 : 1) + (p.cluster ? 1 : 0));
     }
     for (int s = 0; s < 4; ++s) {
       mbar_init(&xf[s], 128);
@@ -282,6 +319,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (p.cluster) cluster_sync_all();              // the peer's barriers exist before anything is multicast at them
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp_idx == 0) {
@@ -296,8 +334,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const uint32_t a_dst = smem_u32(tiles + s * C::STAGE_BYTES);
         const uint32_t b_dst = a_dst + C::A_BYTES;
         load_operand<A_MN, TM>(a_dst, &tmap_a, &full[s], m_blk * BM * TM, k_elem);
-        load_operand<B_MN, TN>(b_dst, &tmap_b, &full[s], n_blk * BN * TN, k_elem);
-        if (BLO) load_operand<B_MN, TN>(b_dst + C::B_BYTES, &tmap_blo, &full[s], n_blk * BN * TN, k_elem);
+        if (p.cluster) {
+          load_operand_mc<B_MN, TN>(b_dst, &tmap_b, &full[s], n_blk * BN * TN, k_elem, crank);
+          if (BLO) load_operand_mc<B_MN, TN>(b_dst + C::B_BYTES, &tmap_blo, &full[s], n_blk * BN * TN, k_elem, crank);
+        } else {
+          load_operand<B_MN, TN>(b_dst, &tmap_b, &full[s], n_blk * BN * TN, k_elem);
+          if (BLO) load_operand<B_MN, TN>(b_dst + C::B_BYTES, &tmap_blo, &full[s], n_blk * BN * TN, k_elem);
+        }
       }
     }
   } else if (warp_idx == 1) {
@@ -331,7 +374,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               umma_tf32_ts(acc, ta_hi + k * UMMA_K, db, idesc, 1u);                                    // A_hi * B_hi
             }
           }
-          umma_commit(&empty[s]);
+          if (p.cluster) umma_commit_mc(&empty[s], (uint16_t)3); else umma_commit(&empty[s]);
           umma_commit(&lo_empty[ls]);
           continue;
         }
@@ -355,7 +398,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
           }
         }
-        umma_commit(&empty[s]);     // frees the operand stage when these MMAs retire
+        if (p.cluster) umma_commit_mc(&empty[s], (uint16_t)3); else umma_commit(&empty[s]);     // frees the operand stage when these MMAs retire
         if (SPLIT3) umma_commit(&lo_empty[ls]);
       }
       umma_commit(tmem_full);       // accumulators complete
@@ -459,6 +502,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (p.cluster) cluster_sync_all();              // stay resident until the peer's last multicast commit has landed here
   if (warp_idx == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -471,10 +515,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // operand with logical shape [mn, k]; kmajor: ptr[mn*ld + k] else ptr[k*ld + mn]; T = tile multiplier
-static int make_operand_map(const nar_ctx* ctx, CUtensorMap* map, const float* ptr, int64_t mn, int64_t k, int64_t ld, bool kmajor, int T) {
+static int make_operand_map(const nar_ctx* ctx, CUtensorMap* map, const float* ptr, int64_t mn, int64_t k, int64_t ld, bool kmajor, int T,
+                            int box_rows = 128) {
   if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0 || (ld & 3) != 0 || ld <= 0) return NAR_ERR_INVALID;
   cuuint64_t dims[2]; cuuint64_t strides[1]; cuuint32_t box[2]; cuuint32_t estr[2] = {1, 1};
-  if (kmajor) { dims[0] = (cuuint64_t)k; dims[1] = (cuuint64_t)mn; box[0] = BK; box[1] = (cuuint32_t)(128 * T); }
+  if (kmajor) { dims[0] = (cuuint64_t)k; dims[1] = (cuuint64_t)mn; box[0] = BK; box[1] = (cuuint32_t)(box_rows * T); }
   else        { dims[0] = (cuuint64_t)mn; dims[1] = (cuuint64_t)k; box[0] = 32; box[1] = BK; }
   strides[0] = (cuuint64_t)ld * 4;
   CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
@@ -492,6 +537,18 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
   if (!attr_set) {
     NAR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE, TM, TN>::SMEM_BYTES));
     attr_set = true;
+  }
+  if (p.cluster) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = Cfg<MODE, TM, TN>::SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    NAR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tbl, p));
+    return NAR_OK;
   }
   kern<<<grid, NUM_THREADS, Cfg<MODE, TM, TN>::SMEM_BYTES, st>>>(ta, tb, tbl, p);
   NAR_LAUNCH_CHECK();
@@ -536,21 +593,30 @@ extern "C" int nar_gemm_tf32(nar_ctx* ctx, int64_t M, int64_t N, int64_t K, cons
   if (split > 1 && !epi->accumulate) return NAR_ERR_INVALID;
   int per = (k_tiles + split - 1) / split;
   split = (k_tiles + per - 1) / per;          // no empty splits
+  // Optional (NAR_GEMM_CLUSTER=1): clusters of 2 CTAs along M share their B tiles through TMA multicast.  Validated
+  // bit-identical, but measured 3-6 % SLOWER on B200 for every shape of the step (24000x1024x1024: 3xTF32 forward 379 ->
+  // 389 us, single pass 194 -> 201 us, 256x256 dgrad 137 -> 142 us): halving the B traffic out of L2 does not help, the
+  // lock-step of the CTA pair costs a little.  Off by default.
+  static int cluster_env = -1;
+  if (cluster_env < 0) { const char* e = getenv("NAR_GEMM_CLUSTER"); cluster_env = e ? atoi(e) : 0; }
+  const bool cluster = cluster_env != 0 && (mode == 0 || mode == 3) && m_tiles >= 2;
+  const int64_t m_tiles_launch = cluster ? (m_tiles + 1) / 2 * 2 : m_tiles;      // an odd tail tile gets a partner that stores nothing
   CUtensorMap ta, tb;
   int rc = make_operand_map(ctx, &ta, A, M, K, lda, a_kmajor != 0, TM);
   if (rc) return rc;
-  rc = make_operand_map(ctx, &tb, B, N, K, ldb, b_kmajor != 0, TN);
+  rc = make_operand_map(ctx, &tb, B, N, K, ldb, b_kmajor != 0, TN, cluster ? 64 : 128);
   if (rc) return rc;
   CUtensorMap tbl = tb;
   if (blo) {
-    rc = make_operand_map(ctx, &tbl, epi->b_lo, N, K, ldb, b_kmajor != 0, TN);
+    rc = make_operand_map(ctx, &tbl, epi->b_lo, N, K, ldb, b_kmajor != 0, TN, cluster ? 64 : 128);
     if (rc) return rc;
   }
   Params p;
   p.M = M; p.N = N; p.K = K; p.D = D; p.ldd = ldd; p.bias = epi->bias; p.aux = epi->aux; p.ld_aux = epi->ld_aux;
   p.act = epi->act; p.dact = epi->dact; p.accumulate = epi->accumulate; p.k_tiles_per_split = per;
   p.n_tiles = (int)n_tiles;
-  dim3 grid((unsigned)(n_tiles * m_tiles), (unsigned)split, 1);
+  p.cluster = cluster ? 1 : 0;
+  dim3 grid((unsigned)(n_tiles * m_tiles_launch), (unsigned)split, 1);
   cudaStream_t st = as_stream(stream);
   const bool amn = !a_kmajor, bmn = !b_kmajor;
 #define NAR_GEMM_CASE(a, b) \

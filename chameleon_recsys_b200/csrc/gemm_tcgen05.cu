@@ -45,7 +45,9 @@ constexpr int NUM_THREADS = 256;
 //           and write A_hi | A_lo into TMEM (tcgen05.st); the MMAs then read only B / B_lo from shared memory.
 //           (MODE 2 re-reads the A slices from shared memory for each of the 3 MMAs and is bound by the shared-
 //           memory port: ~176 KB of smem traffic per k-tile vs ~112 KB here.)  Needs A K-major and a B_lo plane.
-template <int MODE, int TM, int TN> struct Cfg {
+// OCC = 2: half-depth rings so that TWO CTAs are resident per SM - the prologue (barrier init, TMEM alloc, first TMA
+// round trip) and the epilogue of one tile overlap the main loop of the other (the kernel is not persistent).
+template <int MODE, int TM, int TN, int OCC = 1> struct Cfg {
   static constexpr bool SPLIT3 = MODE != 0;
   static constexpr bool BLO = MODE >= 2;
   static constexpr bool ATMEM = MODE == 3;
@@ -53,14 +55,17 @@ template <int MODE, int TM, int TN> struct Cfg {
   static constexpr int B_BYTES = TN * TILE_BYTES_1;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES * (BLO ? 2 : 1);     // one operand stage (A | B [| B_lo])
   static constexpr int LO_STAGE_BYTES = (SPLIT3 && !ATMEM) ? (BLO ? A_BYTES : A_BYTES + B_BYTES) : 0;
-  static constexpr int STAGES = SPLIT3 ? (BLO ? (TM == 2 ? 3 : 4) : 5) : (TM * TN == 4 ? 3 : 6);  // operand ring depth
-  static constexpr int LO_STAGES = SPLIT3 ? (ATMEM ? (TM == 2 ? 2 : 4) : 2) : 0;   // lo ring depth (shared memory, or TMEM for MODE 3)
+  static constexpr int STAGES = OCC == 2 ? ((MODE == 3 || TM * TN == 2) ? 2 : 3)
+                                         : (SPLIT3 ? (BLO ? (TM == 2 ? 3 : 4) : 5) : (TM * TN == 4 ? 3 : 6));  // operand ring depth
+  static constexpr int LO_STAGES = SPLIT3 ? (ATMEM ? ((TM == 2 || OCC == 2) ? 2 : 4) : 2) : 0;   // lo ring depth (shared memory, or TMEM for MODE 3)
   static constexpr int TILE_BYTES = STAGES * STAGE_BYTES + (ATMEM ? 0 : LO_STAGES * LO_STAGE_BYTES);
   static constexpr int SMEM_BYTES = TILE_BYTES + 256 + 1024;                // tiles + barriers + align slack
-  static constexpr int TMEM_COLS = ATMEM ? 512 : TM * TN * 128;             // accumulators (+ A ring: TM x (A_hi | A_lo) of 32 columns per stage)
+  static constexpr int TMEM_COLS = ATMEM ? (OCC == 2 ? 256 : 512) : TM * TN * 128;             // accumulators (+ A ring: TM x (A_hi | A_lo) of 32 columns per stage)
   static constexpr int TMEM_A_BASE = TM * TN * 128;                         // MODE 3: A ring starts after the accumulators
   static_assert((TM == 1 && TN == 1) || MODE == 0 || (MODE == 3 && TM == 2 && TN == 1), "tile shapes: 128x128; 256x256 single pass; 256x128 with A in TMEM");
-  static_assert(!ATMEM || TMEM_A_BASE + LO_STAGES * TM * 64 <= 512, "tensor memory budget");
+  static_assert(!ATMEM || TMEM_A_BASE + LO_STAGES * TM * 64 <= TMEM_COLS, "tensor memory budget");
+  static_assert(OCC == 1 || (TN == 1 && ((TM == 1 && (MODE == 0 || MODE == 3)) || (TM == 2 && MODE == 0))),
+                "two CTAs per SM: 128x128 tiles (single pass or A-in-TMEM) or 256x128 single pass");
 };
 
 struct Params {
@@ -264,11 +269,11 @@ __device__ __forceinline__ void load_operand_mc(uint32_t dst, const CUtensorMap*
 }
 
 // ---------------------------------------------------------------- kernel
-template <bool A_MN, bool B_MN, int MODE, int TM, int TN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <bool A_MN, bool B_MN, int MODE, int TM, int TN, int OCC = 1>
+__global__ void __launch_bounds__(NUM_THREADS, OCC)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_blo, const Params p) {
-  using C = Cfg<MODE, TM, TN>;
+  using C = Cfg<MODE, TM, TN, OCC>;
   constexpr bool SPLIT3 = C::SPLIT3, BLO = C::BLO, ATMEM = C::ATMEM;
   constexpr int LS = C::LO_STAGES > 0 ? C::LO_STAGES : 1;        // lo ring depth (2 in shared memory, 4 in TMEM)
   static_assert(!ATMEM || !A_MN, "A in tensor memory must be K-major");
@@ -530,19 +535,19 @@ static int make_operand_map(const nar_ctx* ctx, CUtensorMap* map, const float* p
   return r == CUDA_SUCCESS ? NAR_OK : NAR_ERR_INVALID;
 }
 
-template <bool A_MN, bool B_MN, int MODE, int TM, int TN>
+template <bool A_MN, bool B_MN, int MODE, int TM, int TN, int OCC = 1>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbl, const Params& p, dim3 grid, cudaStream_t st) {
-  auto kern = gemm_tf32_kernel<A_MN, B_MN, MODE, TM, TN>;
+  auto kern = gemm_tf32_kernel<A_MN, B_MN, MODE, TM, TN, OCC>;
   static bool attr_set = false;     // per instantiation
   if (!attr_set) {
-    NAR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE, TM, TN>::SMEM_BYTES));
+    NAR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE, TM, TN, OCC>::SMEM_BYTES));
     attr_set = true;
   }
   if (p.cluster) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = grid; cfg.blockDim = dim3(NUM_THREADS, 1, 1);
-    cfg.dynamicSmemBytes = Cfg<MODE, TM, TN>::SMEM_BYTES; cfg.stream = st;
+    cfg.dynamicSmemBytes = Cfg<MODE, TM, TN, OCC>::SMEM_BYTES; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -550,7 +555,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     NAR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tbl, p));
     return NAR_OK;
   }
-  kern<<<grid, NUM_THREADS, Cfg<MODE, TM, TN>::SMEM_BYTES, st>>>(ta, tb, tbl, p);
+  kern<<<grid, NUM_THREADS, Cfg<MODE, TM, TN, OCC>::SMEM_BYTES, st>>>(ta, tb, tbl, p);
   NAR_LAUNCH_CHECK();
   return NAR_OK;
 }
@@ -574,8 +579,10 @@ extern "C" int nar_gemm_tf32(nar_ctx* ctx, int64_t M, int64_t N, int64_t K, cons
   // 256x256 CTA tiles for the big single-pass GEMMs (L2-bound with 128x128 tiles); 128x128 otherwise
   const bool big = (double)M * (double)N * (double)K >= 4e9;
   // (256x128 tiles with A in TMEM are implemented and validated but measured ~10 % slower than 128x128 for MODE 3)
+  static int big_env = -1;     // big single-pass GEMMs: 0 = 256x256 tiles, one CTA per SM; 1 = 256x128 tiles, two CTAs per SM
+  if (big_env < 0) { const char* e = getenv("NAR_GEMM_BIG_OCC2"); big_env = e ? atoi(e) : 0; }
   const int TM = (mode == 0 && M >= 256 && N >= 256 && big) ? 2 : 1;
-  const int TN = (mode == 0 && TM == 2) ? 2 : 1;
+  const int TN = (mode == 0 && TM == 2 && !big_env) ? 2 : 1;
   const int64_t n_tiles = (N + BN * TN - 1) / (BN * TN), m_tiles = (M + BM * TM - 1) / (BM * TM);
   if (n_tiles * m_tiles > 0x7fffffffLL) return NAR_ERR_UNSUPPORTED;
   const int k_tiles = (int)((K + BK - 1) / BK);
@@ -619,9 +626,15 @@ extern "C" int nar_gemm_tf32(nar_ctx* ctx, int64_t M, int64_t N, int64_t K, cons
   dim3 grid((unsigned)(n_tiles * m_tiles_launch), (unsigned)split, 1);
   cudaStream_t st = as_stream(stream);
   const bool amn = !a_kmajor, bmn = !b_kmajor;
+  static int occ_env = -1;
+  if (occ_env < 0) { const char* e = getenv("NAR_GEMM_OCC2"); occ_env = e ? atoi(e) : 1; }
+  const bool occ2 = occ_env != 0 && !cluster;
 #define NAR_GEMM_CASE(a, b) \
   if (amn == a && bmn == b) { \
+    if (mode == 0 && TM == 1 && occ2) return launch<a, b, 0, 1, 1, 2>(ta, tb, tbl, p, grid, st); \
+    if (mode == 3 && TM == 1 && occ2) return launch<false, b, 3, 1, 1, 2>(ta, tb, tbl, p, grid, st); \
     if (mode == 0 && TM == 1) return launch<a, b, 0, 1, 1>(ta, tb, tbl, p, grid, st); \
+    if (mode == 0 && TM == 2 && TN == 1) return launch<a, b, 0, 2, 1, 2>(ta, tb, tbl, p, grid, st); \
     if (mode == 0 && TM == 2) return launch<a, b, 0, 2, 2>(ta, tb, tbl, p, grid, st); \
     if (mode == 1) return launch<a, b, 1, 1, 1>(ta, tb, tbl, p, grid, st); \
     if (mode == 2) return launch<a, b, 2, 1, 1>(ta, tb, tbl, p, grid, st); \

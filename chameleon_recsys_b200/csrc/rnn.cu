@@ -37,7 +37,69 @@ __device__ __forceinline__ Sess load_sessions(const int32_t* __restrict__ sess_o
     s.len[i] = b < B ? sess_off[b + 1] - sess_off[b] : 0;
     s.maxlen = max(s.maxlen, s.len[i]);
   }
+  // longest first: at step t the sessions still running are slots [0, na) - the recurrent product skips the rest.
+  // (The step count of a CTA is set by its longest session; with G1's geometric session lengths most slots are idle
+  // after a few steps, and doing all SB products anyway made the whole kernel 19 x full-cost steps long.)
+#pragma unroll
+  for (int a = 0; a < SB - 1; ++a)
+#pragma unroll
+    for (int b = 0; b < SB - 1 - a; ++b)
+      if (s.len[b] < s.len[b + 1]) {
+        const int tl = s.len[b], to = s.off[b];
+        s.len[b] = s.len[b + 1]; s.off[b] = s.off[b + 1];
+        s.len[b + 1] = tl; s.off[b + 1] = to;
+      }
   return s;
+}
+__device__ __forceinline__ int active_sessions(const Sess& s, int t) {
+  int na = 0;
+#pragma unroll
+  for (int i = 0; i < SB; ++i) na += (s.len[i] > t) ? 1 : 0;
+  return na;
+}
+
+// h[0..NA) * Wh slice of this thread -> partial sums in shared memory
+template <int NA>
+__device__ __forceinline__ void fwd_product(const float* __restrict__ Wh, const float* h, float* part, int Hp, int k0, int kspan,
+                                            int jc, int kq) {
+  const int W2 = 2 * Hp;
+  float4 ag[NA], ac[NA];
+#pragma unroll
+  for (int s = 0; s < NA; ++s) { ag[s] = make_float4(0.f, 0.f, 0.f, 0.f); ac[s] = ag[s]; }
+  const float4* wg = reinterpret_cast<const float4*>(Wh + (int64_t)k0 * W2) + jc;
+  const float4* wc = reinterpret_cast<const float4*>(Wh + (int64_t)k0 * W2 + Hp) + jc;
+  const int stride4 = W2 >> 2;
+#pragma unroll 8
+  for (int k = 0; k < kspan; ++k) {
+    const float4 a = __ldg(wg + (int64_t)k * stride4), c = __ldg(wc + (int64_t)k * stride4);
+#pragma unroll
+    for (int s = 0; s < NA; ++s) { const float hv = h[s * Hp + k0 + k]; fma4(ag[s], hv, a); fma4(ac[s], hv, c); }
+  }
+#pragma unroll
+  for (int s = 0; s < NA; ++s) {
+    float4* pg = reinterpret_cast<float4*>(part + ((kq * SB + s) * 2 + 0) * Hp) + jc;
+    float4* pc = reinterpret_cast<float4*>(part + ((kq * SB + s) * 2 + 1) * Hp) + jc;
+    *pg = ag[s]; *pc = ac[s];
+  }
+}
+
+template <int NA>
+__device__ __forceinline__ void bwd_product(const float* __restrict__ WhT, const float* dact, float* part, int Hp, int j0, int jspan,
+                                            int kc, int jq) {
+  const int W2 = 2 * Hp;
+  float4 acc[NA];
+#pragma unroll
+  for (int s = 0; s < NA; ++s) acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* w = reinterpret_cast<const float4*>(WhT + (int64_t)j0 * Hp) + kc;
+  const int stride4 = Hp >> 2;
+#pragma unroll 8
+  for (int j = 0; j < jspan; ++j) {
+    const float4 a = __ldg(w + (int64_t)j * stride4);
+#pragma unroll
+    for (int s = 0; s < NA; ++s) fma4(acc[s], dact[s * W2 + j0 + j], a);
+  }
+#pragma unroll
+  for (int s = 0; s < NA; ++s) *(reinterpret_cast<float4*>(part + (jq * SB + s) * Hp) + kc) = acc[s];
 }
 
 // shared: h[SB][Hp] | part[NSPLIT][SB][2][Hp]
@@ -57,24 +119,12 @@ ugrnn_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ Wh, con
   __syncthreads();
   for (int t = 0; t < ss.maxlen; ++t) {
     if (t > 0) {
-      float4 ag[SB], ac[SB];
-#pragma unroll
-      for (int s = 0; s < SB; ++s) { ag[s] = make_float4(0.f, 0.f, 0.f, 0.f); ac[s] = ag[s]; }
-      const float4* wg = reinterpret_cast<const float4*>(Wh + (int64_t)k0 * W2) + jc;
-      const float4* wc = reinterpret_cast<const float4*>(Wh + (int64_t)k0 * W2 + Hp) + jc;
-      const int stride4 = W2 >> 2;
-#pragma unroll 8
-      for (int k = 0; k < kspan; ++k) {
-        const float4 a = __ldg(wg + (int64_t)k * stride4), c = __ldg(wc + (int64_t)k * stride4);
-#pragma unroll
-        for (int s = 0; s < SB; ++s) { const float hv = h[s * Hp + k0 + k]; fma4(ag[s], hv, a); fma4(ac[s], hv, c); }
-      }
-#pragma unroll
-      for (int s = 0; s < SB; ++s) {
-        float4* pg = reinterpret_cast<float4*>(part + ((kq * SB + s) * 2 + 0) * Hp) + jc;
-        float4* pc = reinterpret_cast<float4*>(part + ((kq * SB + s) * 2 + 1) * Hp) + jc;
-        *pg = ag[s]; *pc = ac[s];
-      }
+      // sessions that reach step t also had step t-1, so slots [0, na) are exactly the ones with a live state
+      const int na = active_sessions(ss, t);
+      if (na <= 1) fwd_product<1>(Wh, h, part, Hp, k0, kspan, jc, kq);
+      else if (na <= 2) fwd_product<2>(Wh, h, part, Hp, k0, kspan, jc, kq);
+      else if (na <= 4) fwd_product<4>(Wh, h, part, Hp, k0, kspan, jc, kq);
+      else fwd_product<SB>(Wh, h, part, Hp, k0, kspan, jc, kq);
     }
     __syncthreads();
     // finalise: thread j owns column j of every session
@@ -146,19 +196,11 @@ ugrnn_bwd_kernel(const float* __restrict__ d_hout, const float* __restrict__ h_o
     }
     __syncthreads();
     if (t > 0) {
-      float4 acc[SB];
-#pragma unroll
-      for (int s = 0; s < SB; ++s) acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4* w = reinterpret_cast<const float4*>(WhT + (int64_t)j0 * Hp) + kc;
-      const int stride4 = Hp >> 2;
-#pragma unroll 8
-      for (int j = 0; j < jspan; ++j) {
-        const float4 a = __ldg(w + (int64_t)j * stride4);
-#pragma unroll
-        for (int s = 0; s < SB; ++s) fma4(acc[s], dact[s * W2 + j0 + j], a);
-      }
-#pragma unroll
-      for (int s = 0; s < SB; ++s) *(reinterpret_cast<float4*>(part + (jq * SB + s) * Hp) + kc) = acc[s];
+      const int na = active_sessions(ss, t);          // d_act of the slots past na is zero at this step
+      if (na <= 1) bwd_product<1>(WhT, dact, part, Hp, j0, jspan, kc, jq);
+      else if (na <= 2) bwd_product<2>(WhT, dact, part, Hp, j0, jspan, kc, jq);
+      else if (na <= 4) bwd_product<4>(WhT, dact, part, Hp, j0, jspan, kc, jq);
+      else bwd_product<SB>(WhT, dact, part, Hp, j0, jspan, kc, jq);
       __syncthreads();
       for (int k = threadIdx.x; k < Hp; k += THREADS) {
 #pragma unroll

@@ -44,20 +44,36 @@ def launches(src, dst):
     print('wrote', dst)
 
 
-def full(src, dst):
+UNIT = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+
+
+def full(src, dst, traffic_key=None):
     out = subprocess.run(['ncu', '-i', src, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
+    traffic = None
     with open(dst, 'w') as f:
         for vals in rows[2:]:
             d = dict(zip(hdr, vals))
             f.write('kernel: %s\n' % d.get('Kernel Name', '?'))
+            tot = 0.0
             for h, u, v in zip(hdr, units, vals):
                 if h in KEEP:
                     f.write('  %-86s %-14s %s\n' % (h, u, v))
+                if h in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+                    tot += float(v.replace(',', '')) * UNIT.get(u, 1.0)
             f.write('\n')
+            traffic = tot
     print('wrote', dst)
+    if traffic_key:
+        import json
+        import os
+        p = os.path.join(os.path.dirname(os.path.abspath(dst)), 'ncu_traffic.json')
+        d = json.load(open(p)) if os.path.exists(p) else {}
+        d[traffic_key] = traffic
+        json.dump(d, open(p, 'w'), indent=1, sort_keys=True)
+        print('traffic[%s] = %.0f bytes -> %s' % (traffic_key, traffic, p))
 
 
 if __name__ == '__main__':
-    {'launches': launches, 'full': full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {'launches': launches, 'full': full}[sys.argv[1]](*sys.argv[2:])

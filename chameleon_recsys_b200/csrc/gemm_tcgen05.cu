@@ -64,8 +64,8 @@ template <int MODE, int TM, int TN, int OCC = 1> struct Cfg {
   static constexpr int TMEM_A_BASE = TM * TN * 128;                         // MODE 3: A ring starts after the accumulators
   static_assert((TM == 1 && TN == 1) || MODE == 0 || (MODE == 3 && TM == 2 && TN == 1), "tile shapes: 128x128; 256x256 single pass; 256x128 with A in TMEM");
   static_assert(!ATMEM || TMEM_A_BASE + LO_STAGES * TM * 64 <= TMEM_COLS, "tensor memory budget");
-  static_assert(OCC == 1 || (TN == 1 && ((TM == 1 && (MODE == 0 || MODE == 3)) || (TM == 2 && MODE == 0))),
-                "two CTAs per SM: 128x128 tiles (single pass or A-in-TMEM) or 256x128 single pass");
+  static_assert(OCC == 1 || (TM * TN == 1 && (MODE == 0 || MODE == 3)) || (TM * TN == 2 && MODE == 0),
+                "two CTAs per SM: 128x128 tiles (single pass or A-in-TMEM), 256x128 or 128x256 single pass");
 };
 
 struct Params {
@@ -579,10 +579,15 @@ extern "C" int nar_gemm_tf32(nar_ctx* ctx, int64_t M, int64_t N, int64_t K, cons
   // 256x256 CTA tiles for the big single-pass GEMMs (L2-bound with 128x128 tiles); 128x128 otherwise
   const bool big = (double)M * (double)N * (double)K >= 4e9;
   // (256x128 tiles with A in TMEM are implemented and validated but measured ~10 % slower than 128x128 for MODE 3)
-  static int big_env = -1;     // big single-pass GEMMs: 0 = 256x256 tiles, one CTA per SM; 1 = 256x128 tiles, two CTAs per SM
-  if (big_env < 0) { const char* e = getenv("NAR_GEMM_BIG_OCC2"); big_env = e ? atoi(e) : 0; }
-  const int TM = (mode == 0 && M >= 256 && N >= 256 && big) ? 2 : 1;
-  const int TN = (mode == 0 && TM == 2 && !big_env) ? 2 : 1;
+  // big single-pass GEMMs: 0 = 256x256 tiles, one CTA per SM; 1 = 256x128 tiles, 2 = 128x256 tiles, two CTAs per SM
+  // (measured, 24000x1024x1024: dgrad 135 / 122 / 111 us, dgrad + activation derivative 178 / 143 / 134 us, wgrad
+  // 143 / 144 / 135 us: one 128x256x8 MMA reads 12 KB of shared memory per 2x the math of a 128x128x8 one (8 KB), and
+  // the second resident CTA hides the epilogue)
+  static int big_env = -1;
+  if (big_env < 0) { const char* e = getenv("NAR_GEMM_BIG_OCC2"); big_env = e ? atoi(e) : 2; }
+  const bool bigtile = mode == 0 && M >= 256 && N >= 256 && big;
+  const int TM = (bigtile && big_env != 2) ? 2 : 1;
+  const int TN = (bigtile && big_env != 1) ? 2 : 1;
   const int64_t n_tiles = (N + BN * TN - 1) / (BN * TN), m_tiles = (M + BM * TM - 1) / (BM * TM);
   if (n_tiles * m_tiles > 0x7fffffffLL) return NAR_ERR_UNSUPPORTED;
   const int k_tiles = (int)((K + BK - 1) / BK);
@@ -631,6 +636,7 @@ extern "C" int nar_gemm_tf32(nar_ctx* ctx, int64_t M, int64_t N, int64_t K, cons
   const bool occ2 = occ_env != 0 && !cluster;
 #define NAR_GEMM_CASE(a, b) \
   if (amn == a && bmn == b) { \
+    if (mode == 0 && TM == 1 && TN == 2) return launch<a, b, 0, 1, 2, 2>(ta, tb, tbl, p, grid, st); \
     if (mode == 0 && TM == 1 && occ2) return launch<a, b, 0, 1, 1, 2>(ta, tb, tbl, p, grid, st); \
     if (mode == 3 && TM == 1 && occ2) return launch<false, b, 3, 1, 1, 2>(ta, tb, tbl, p, grid, st); \
     if (mode == 0 && TM == 1) return launch<a, b, 0, 1, 1>(ta, tb, tbl, p, grid, st); \

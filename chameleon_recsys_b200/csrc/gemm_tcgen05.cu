@@ -577,7 +577,7 @@ extern "C" int nar_gemm_tf32(nar_ctx* ctx, int64_t M, int64_t N, int64_t K, cons
   const bool blo = epi->precision == 3 && epi->b_lo != nullptr;
   const int mode = epi->precision == 1 ? 0 : (blo ? (a_kmajor ? 3 : 2) : 1);
   // 256x256 CTA tiles for the big single-pass GEMMs (L2-bound with 128x128 tiles); 128x128 otherwise
-  const bool big = (double)M * (double)N * (double)K >= 4e9;
+  const bool big = (double)M * (double)N * (double)K >= 2e9;
   // (256x128 tiles with A in TMEM are implemented and validated but measured ~10 % slower than 128x128 for MODE 3)
   // big single-pass GEMMs: 0 = 256x256 tiles, one CTA per SM; 1 = 256x128 tiles, 2 = 128x256 tiles, two CTAs per SM
   // (measured, 24000x1024x1024: dgrad 135 / 122 / 111 us, dgrad + activation derivative 178 / 143 / 134 us, wgrad

@@ -320,18 +320,32 @@ gather_features_bwd_kernel(const __grid_constant__ nar_feature_plan P, const int
     const int j = c - sg.col;
     const float gam = P.gamma[c];
     float acc_b = 0.f, acc_g = 0.f;
-    for (int i = 0; i < nr; ++i) {
-      const float d = d_out[(r0 + i) * (int64_t)P.row_ld + c];
-      const float raw = seg_value(P, sg, j, s_pos[i], s_item[i], s_ts[i], P.stats + 8 * s_grp[i]);
-      acc_b += d;
-      acc_g += d * raw;
-      if (sg.grad != nullptr) {
-        int64_t id;
-        if (sg.kind == NAR_SEG_ITEM_EMB) id = s_item[i];
-        else if (sg.kind == NAR_SEG_CTX_EMBED) id = P.ctx_int[sg.src][s_pos[i]];
-        else id = P.meta[sg.src][s_item[i]];
-        if (sg.kind != NAR_SEG_ITEM_EMB) id = id < 0 ? 0 : (id >= sg.card ? sg.card - 1 : id);
-        atomicAdd(sg.grad + id * (int64_t)sg.ld + j, d * gam);
+    // 4 rows per trip: the 8 loads (dX, re-gathered raw value) are issued before the first atomic - the compiler may
+    // not move loads across the atomics itself (they could alias the tables)
+    for (int i0 = 0; i0 < nr; i0 += 4) {
+      float d[4], raw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u;
+        d[u] = 0.f; raw[u] = 0.f;
+        if (i < nr) {
+          d[u] = __ldg(d_out + (r0 + i) * (int64_t)P.row_ld + c);
+          raw[u] = seg_value(P, sg, j, s_pos[i], s_item[i], s_ts[i], P.stats + 8 * s_grp[i]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u;
+        acc_b += d[u];
+        acc_g += d[u] * raw[u];
+        if (sg.grad != nullptr && i < nr) {
+          int64_t id;
+          if (sg.kind == NAR_SEG_ITEM_EMB) id = s_item[i];
+          else if (sg.kind == NAR_SEG_CTX_EMBED) id = P.ctx_int[sg.src][s_pos[i]];
+          else id = P.meta[sg.src][s_item[i]];
+          if (sg.kind != NAR_SEG_ITEM_EMB) id = id < 0 ? 0 : (id >= sg.card ? sg.card - 1 : id);
+          atomicAdd(sg.grad + id * (int64_t)sg.ld + j, d[u] * gam);
+        }
       }
     }
     atomicAdd(d_beta + c, acc_b);

@@ -15,7 +15,7 @@
 namespace nar {
 namespace rnn {
 
-constexpr int SB = 8;             // sessions per CTA
+constexpr int SB = 4;             // sessions per CTA (8 -> 4: 64 CTAs at batch 256, and the early all-active steps cost half)
 constexpr int THREADS = 256;
 constexpr int MAX_HP = 1024;
 
@@ -123,7 +123,6 @@ ugrnn_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ Wh, con
       const int na = active_sessions(ss, t);
       if (na <= 1) fwd_product<1>(Wh, h, part, Hp, k0, kspan, jc, kq);
       else if (na <= 2) fwd_product<2>(Wh, h, part, Hp, k0, kspan, jc, kq);
-      else if (na <= 4) fwd_product<4>(Wh, h, part, Hp, k0, kspan, jc, kq);
       else fwd_product<SB>(Wh, h, part, Hp, k0, kspan, jc, kq);
     }
     __syncthreads();
@@ -199,7 +198,6 @@ ugrnn_bwd_kernel(const float* __restrict__ d_hout, const float* __restrict__ h_o
       const int na = active_sessions(ss, t);          // d_act of the slots past na is zero at this step
       if (na <= 1) bwd_product<1>(WhT, dact, part, Hp, j0, jspan, kc, jq);
       else if (na <= 2) bwd_product<2>(WhT, dact, part, Hp, j0, jspan, kc, jq);
-      else if (na <= 4) bwd_product<4>(WhT, dact, part, Hp, j0, jspan, kc, jq);
       else bwd_product<SB>(WhT, dact, part, Hp, j0, jspan, kc, jq);
       __syncthreads();
       for (int k = threadIdx.x; k < Hp; k += THREADS) {

@@ -160,6 +160,43 @@ cosine_softmax_ce_kernel(const float* __restrict__ cand, const float* __restrict
   }
 }
 
+
+// ---------------------------------------------------------------- evaluation ranking
+// one warp per position: softmax probabilities in shared memory, rank of candidate i = number of candidates that
+// precede it in tf.nn.top_k order (higher probability, or equal probability and lower index).
+constexpr int RANK_WARPS = 4;
+
+__global__ void __launch_bounds__(RANK_WARPS * 32)
+rank_candidates_kernel(const float* __restrict__ logits, const int64_t* __restrict__ cand_ids, int64_t n_pos, int n_cand,
+                       int top_n, int64_t* __restrict__ pred_ids, float* __restrict__ pred_probs, float* __restrict__ metrics) {
+  extern __shared__ float sh[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t l = (int64_t)blockIdx.x * RANK_WARPS + w;
+  if (l >= n_pos) return;
+  float* p = sh + (size_t)w * n_cand;
+  const float* lg = logits + l * n_cand;
+  float mx = -INFINITY;
+  for (int j = lane; j < n_cand; j += 32) mx = fmaxf(mx, lg[j]);
+  mx = warp_max(mx);
+  float se = 0.f;
+  for (int j = lane; j < n_cand; j += 32) { const float e = expf(lg[j] - mx); p[j] = e; se += e; }
+  se = warp_sum(se);
+  __syncwarp();
+  for (int j = lane; j < n_cand; j += 32) p[j] = p[j] / se;
+  __syncwarp();
+  for (int i = lane; i < n_cand; i += 32) {
+    const float pi = p[i];
+    int rank = 0;
+    for (int j = 0; j < n_cand; ++j) { const float pj = p[j]; rank += (pj > pi || (pj == pi && j < i)) ? 1 : 0; }
+    if (pred_ids) pred_ids[l * n_cand + rank] = cand_ids[l * n_cand + i];
+    if (pred_probs) pred_probs[l * n_cand + rank] = pi;
+    if (i == 0 && metrics) {
+      if (rank < top_n) { atomicAdd(metrics + 0, 1.0f); atomicAdd(metrics + 1, 1.0f / (float)(rank + 1)); }
+      atomicAdd(metrics + 2, 1.0f);
+    }
+  }
+}
+
 }  // namespace loss
 }  // namespace nar
 
@@ -208,6 +245,20 @@ extern "C" int nar_cosine_softmax_ce(const float* cand, const float* pred, int64
   if (smem > 48 * 1024) return NAR_ERR_UNSUPPORTED;
   nar::loss::cosine_softmax_ce_kernel<<<(unsigned)n_pos, nar::loss::COS_THREADS, smem, as_stream(stream)>>>(
       cand, pred, n_cand, (int)C, inv_temperature, inv_count, logits, loss_sum, d_cand, d_pred);
+  NAR_LAUNCH_CHECK();
+  return NAR_OK;
+}
+
+extern "C" int nar_rank_candidates(const float* logits, const int64_t* cand_ids, int64_t n_pos, int64_t n_cand, int32_t top_n,
+                                   int64_t* pred_ids, float* pred_probs, float* metrics, void* stream) {
+  if (!logits || !cand_ids) return NAR_ERR_INVALID;
+  if (n_pos <= 0) return NAR_OK;
+  if (n_cand <= 0 || top_n < 0) return NAR_ERR_INVALID;
+  const size_t smem = (size_t)nar::loss::RANK_WARPS * n_cand * sizeof(float);
+  if (smem > 48 * 1024) return NAR_ERR_UNSUPPORTED;
+  const unsigned grid = (unsigned)((n_pos + nar::loss::RANK_WARPS - 1) / nar::loss::RANK_WARPS);
+  nar::loss::rank_candidates_kernel<<<grid, nar::loss::RANK_WARPS * 32, smem, as_stream(stream)>>>(
+      logits, cand_ids, n_pos, (int)n_cand, (int)top_n, pred_ids, pred_probs, metrics);
   NAR_LAUNCH_CHECK();
   return NAR_OK;
 }

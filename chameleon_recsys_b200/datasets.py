@@ -7,9 +7,9 @@ feature; ``make_dataset`` (:100-143) zero-pads to the batch maximum (``padded_ba
 no shuffling; ``deflate_and_split_features_label`` (:84-97) splits features / labels;
 dtypes follow utils.get_tf_dtype (:59-68): int -> int64, float -> float32.
 
-The TFRecord/GZIP/protobuf decode itself is a "next" row; the
-source here is any iterable of per-session dicts in the on-disk schema
-(nar_preprocess_gcom.py:75-108), e.g. ``synthetic.SessionStream``.
+The source is either TFRecord files of ``SequenceExample`` protos in the reference's on-disk schema
+(nar_preprocess_gcom.py:75-108; decoded by ``tfrecords.py`` - framing, CRC-32C, gzip and the protobuf wire format,
+no TensorFlow) or any iterable of already-decoded per-session dicts, e.g. ``synthetic.SessionStream``.
 """
 from __future__ import annotations
 
@@ -100,7 +100,11 @@ class OneShotIterator:
 
 
 def prepare_dataset_iterator(files, features_config, batch_size=128, truncate_session_length=20):
-    """datasets.py:166-179.  ``files`` is an iterable of decoded session dicts (see module doc).
+    """datasets.py:166-179.  ``files``: a TFRecord path / glob pattern / list of paths like the reference takes
+    (nar_trainer_gcom.py:511-516), or an iterable of decoded session dicts (see module doc).
     Returns a one-shot iterator whose ``get_next()`` yields ``(features, labels)``."""
+    if isinstance(files, str) or (isinstance(files, (list, tuple)) and files and all(isinstance(f, str) for f in files)):
+        from .tfrecords import read_sequence_examples
+        files = read_sequence_examples(files)
     return OneShotIterator(make_dataset(files, features_config, batch_size=batch_size,
                                         truncate_sequence_length=truncate_session_length))

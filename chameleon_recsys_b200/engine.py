@@ -507,6 +507,46 @@ class NarEngine:
         out['total_loss'] = out['xe_loss'] + out['reg_loss']
         return out
 
+    # ---- evaluation (ModeKeys.EVAL): forward + ranking of the 1+K candidates + HR@n / MRR@n accumulators
+    def share_params(self, other: 'NarEngine'):
+        """Use ``other``'s weights (same ParamLayout) without a copy: what Estimator.evaluate does when it restores the
+        training graph's variables into the evaluation graph (nar_trainer_gcom.py:523)."""
+        if other.layout.total != self.layout.total:
+            raise ValueError('parameter layouts differ')
+        self.params, self.params_lo = other.params, other.params_lo
+        self.global_step = other.global_step
+        self._views = {}
+        self._planc_static = None
+
+    def eval_step(self, features, labels, buffer, pop_norm, top_n: int, metrics: Optional[torch.Tensor] = None,
+                  step_id: Optional[int] = None, keep: bool = False) -> dict:
+        """One evaluation batch: negatives with this engine's (eval) sampling hparams, forward, loss, then
+        rank_items_by_predicted_prob (nar_model.py:777-795) and the streaming HR@n / MRR@n sums (:835-885).
+        ``metrics`` [3] float32 device accumulator {hits, sum of reciprocal ranks, valid labels}."""
+        st = self.stage(features, labels, buffer, pop_norm, slot='eval')
+        if step_id is not None:
+            self.prepare(st, step_id)
+            st['prep']['step_id'] = self.global_step + 1          # step() checks the id it would use itself
+        out = self.step(st, train=False, keep=keep)
+        L, n_cand = st['L'], self.K + 1
+        if metrics is None:
+            metrics = torch.zeros(3, device=self.dev)
+        out['metrics'] = metrics
+        if L > 0:
+            prep = st['prep']
+            pred_ids = self._buf('pred_ids', L, n_cand, torch.int64, cap_rows=st['B'] * st['T'])
+            pred_probs = self._buf('pred_probs', L, n_cand, cap_rows=st['B'] * st['T'])
+            ops.rank_candidates(out['logits'], prep['row_item'][L:], L, n_cand, int(top_n), pred_ids, pred_probs, metrics)
+            out['predicted_item_ids'], out['predicted_item_probs'] = pred_ids, pred_probs
+        if self.world > 1:
+            torch.distributed.all_reduce(self.loss_dev, group=self.pg)
+        self.loss_host.copy_(self.loss_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        out['xe_loss'] = float(self.loss_host[0]); out['reg_loss'] = float(self.loss_host[1])
+        out['total_loss'] = out['xe_loss'] + out['reg_loss']
+        out['stage'] = st
+        return out
+
     def train_step(self, features, labels, buffer, pop_norm, keep: bool = False, sync: bool = True) -> dict:
         st = self.stage(features, labels, buffer, pop_norm)
         self.grads.zero_()

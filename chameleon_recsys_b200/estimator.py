@@ -18,6 +18,7 @@ from typing import Callable, Dict, List, Optional
 
 import numpy as np
 
+from . import checkpoint as ckpt
 from .clicked_items_state import ClickedItemsState
 from .datasets import OutOfRangeError
 from .hparams import ModeKeys, get_internal_enabled_features_config
@@ -94,7 +95,14 @@ def nar_module_model_fn(features, labels, mode, params) -> EstimatorSpec:
         def train_op(feats, labs, feed, sync=True):
             return model.train(feats, labs, feed['pop_recent_items_buffer'], feed['articles_recent_pop_norm'], sync=sync)
         return EstimatorSpec(mode, loss=None, train_op=train_op, training_chief_hooks=hooks, model=model)
-    raise NotImplementedError('ModeKeys.EVAL is a "next" row (SURVEY.md section 8f #2)')
+
+    # ModeKeys.EVAL (nar_trainer_gcom.py:323-332): loss + eval_metric_ops {hitrate_at_n, mrr_at_n}; each "update op" is
+    # one call of model.evaluate, the values are read from the device accumulator at the end
+    def eval_update(feats, labs, feed, metrics, step_id=None):
+        return model.evaluate(feats, labs, feed['pop_recent_items_buffer'], feed['articles_recent_pop_norm'],
+                              metrics=metrics, step_id=step_id)
+    return EstimatorSpec(mode, loss=None, eval_metric_ops={'hitrate_at_n': eval_update, 'mrr_at_n': eval_update},
+                         evaluation_hooks=hooks, model=model)
 
 
 class Estimator:
@@ -105,13 +113,33 @@ class Estimator:
         self.params = params
         self.model_dir = model_dir
         self._spec: Optional[EstimatorSpec] = None
+        self._eval_spec: Optional[EstimatorSpec] = None
         self.last_loss = None
         self.interactions = 0
 
     def _ensure_spec(self, features, labels) -> EstimatorSpec:
         if self._spec is None:
             self._spec = self.model_fn(features, labels, ModeKeys.TRAIN, self.params)
+            latest = ckpt.latest_checkpoint(self.model_dir)          # Estimator semantics: warm-start from model_dir
+            if latest is not None:
+                ckpt.restore(latest, self._spec.model.engine, self._state())
         return self._spec
+
+    def _state(self) -> Optional[ClickedItemsState]:
+        return self.params.get('clicked_items_state') or clicked_items_state
+
+    def save_checkpoint(self, path: Optional[str] = None) -> str:
+        """Write weights + TF-Adam slots + global_step + ClickedItemsState (checkpoint.py); default name
+        ``<model_dir>/model.ckpt-<global_step>.npz``."""
+        eng = self._spec.model.engine
+        if path is None:
+            if not self.model_dir:
+                raise ValueError('no model_dir and no path')
+            path = ckpt.checkpoint_path(self.model_dir, eng.global_step)
+        return ckpt.save(path, eng, self._state())
+
+    def restore_checkpoint(self, path: str) -> int:
+        return ckpt.restore(path, self._spec.model.engine, self._state())
 
     def train(self, input_fn, steps: Optional[int] = None, hooks=None):
         """hook.before_run -> train_op -> hook.after_run per batch (MonitoredTrainingSession), software-pipelined:
@@ -161,7 +189,57 @@ class Estimator:
             self.interactions += int(out['stage']['L_global'])
         for h in spec.training_chief_hooks:
             h.end()
+        if self.model_dir:
+            self.save_checkpoint()                                   # CheckpointSaverHook at the end of train()
         return self
+
+    def evaluate(self, input_fn, steps: Optional[int] = None, hooks=None, name=None) -> dict:
+        """tf.estimator.Estimator.evaluate: runs the EVAL graph over ``input_fn`` with the current weights and returns
+        ``{'loss', 'hitrate_at_n', 'mrr_at_n', 'global_step'}`` (streaming means over all valid labels, nar_model.py:
+        835-885; ``loss`` = mean of the per-batch total_loss like Estimator does).  The hook snapshots ClickedItemsState at
+        ``begin`` and restores it at ``end`` (nar_model.py:1415, :1693), and keeps updating it batch by batch in between."""
+        import torch
+        it = input_fn()
+
+        def fetch():
+            try:
+                return it.get_next() if hasattr(it, 'get_next') else next(it)
+            except (OutOfRangeError, StopIteration):
+                return None
+
+        nxt = fetch() if (steps is None or steps > 0) else None
+        if nxt is None:
+            return {'loss': float('nan'), 'hitrate_at_n': float('nan'), 'mrr_at_n': float('nan'),
+                    'global_step': 0 if self._spec is None else self._spec.model.global_step()}
+        if self._eval_spec is None:
+            self._eval_spec = self.model_fn(nxt[0], nxt[1], ModeKeys.EVAL, self.params)
+        spec = self._eval_spec
+        if self._spec is not None:
+            spec.model.engine.share_params(self._spec.model.engine)        # "restore the latest checkpoint"
+        for h in spec.evaluation_hooks:
+            h.begin()
+        metrics = torch.zeros(3, device=spec.model.engine.dev)
+        update = spec.eval_metric_ops['hitrate_at_n']
+        n, loss_sum = 0, 0.0
+        while nxt is not None:
+            features, labels = nxt
+            feed = {}
+            for h in spec.evaluation_hooks:
+                feed.update(h.before_run(None))
+            out = update(features, labels, feed, metrics, step_id=n + 1)
+            run_values = {'clicked_items': features['item_clicked'], 'clicked_timestamps': features['event_timestamp'],
+                          'last_item_label': labels['label_last_item']}
+            for h in spec.evaluation_hooks:
+                h.after_run(None, run_values)
+            loss_sum += out['total_loss']
+            n += 1
+            nxt = fetch() if (steps is None or n < steps) else None
+        for h in spec.evaluation_hooks:
+            h.end()
+        m = metrics.cpu().numpy()
+        cnt = max(float(m[2]), 1.0)
+        return {'loss': loss_sum / max(n, 1), 'hitrate_at_n': float(m[0]) / cnt, 'mrr_at_n': float(m[1]) / cnt,
+                'global_step': spec.model.global_step()}
 
     @property
     def model(self) -> Optional[NARModuleModel]:

@@ -98,6 +98,8 @@ class NARModuleModel:
         self.user_id = None
         self.batch_negative_items = None
         self.total_loss = None
+        self.predicted_item_ids = None
+        self.predicted_item_probs = None
         self._features = inputs
         self._labels = labels
         self._last = None
@@ -107,6 +109,17 @@ class NARModuleModel:
               articles_recent_pop_norm: np.ndarray, sync: bool = True) -> dict:
         out = self.engine.train_step(features, labels, pop_recent_items_buffer, articles_recent_pop_norm, sync=sync)
         self._publish(features, labels, out)
+        return out
+
+    def evaluate(self, features: Dict[str, np.ndarray], labels: Dict[str, np.ndarray], pop_recent_items_buffer: np.ndarray,
+                 articles_recent_pop_norm: np.ndarray, metrics=None, step_id=None) -> dict:
+        """One EVAL batch (the eval_metric_ops update): loss, ``predicted_item_ids`` / ``predicted_item_probs``
+        (nar_model.py:520-524) and the HR@n / MRR@n accumulators (:835-885) for ``metrics_top_n``."""
+        out = self.engine.eval_step(features, labels, pop_recent_items_buffer, articles_recent_pop_norm,
+                                    top_n=self.metrics_top_n, metrics=metrics, step_id=step_id)
+        self._publish(features, labels, out)
+        self.predicted_item_ids = out.get('predicted_item_ids')
+        self.predicted_item_probs = out.get('predicted_item_probs')
         return out
 
     def _publish(self, features, labels, out):

@@ -168,6 +168,13 @@ def cosine_softmax_ce(cand, pred, n_pos, n_cand, Cdim, inv_temp, inv_count, logi
                                             _p(loss_sum), _p(d_cand), _p(d_pred), _stream()), 'nar_cosine_softmax_ce')
 
 
+def rank_candidates(logits, cand_ids, n_pos, n_cand, top_n, pred_ids, pred_probs, metrics):
+    global LAUNCHES
+    LAUNCHES += 1
+    check(_lib.load().nar_rank_candidates(_p(logits), _p(cand_ids), n_pos, n_cand, top_n, _p(pred_ids), _p(pred_probs),
+                                          _p(metrics), _stream()), 'nar_rank_candidates')
+
+
 def colsum_add(x, rows, cols, ld, out):
     global LAUNCHES
     LAUNCHES += 1

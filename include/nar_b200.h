@@ -200,6 +200,15 @@ int nar_cosine_softmax_ce(const float* cand, const float* pred, int64_t n_pos, i
                           float inv_temperature, float inv_count, float* logits, float* loss_sum,
                           float* d_cand, float* d_pred, void* stream);
 
+/* ---- evaluation ranking (ModeKeys.EVAL: rank_items_by_predicted_prob nar_model.py:777-795 = tf.nn.top_k over all
+ *      1+K candidates, sparse_recall_at_top_k :835-840, define_mrr_metric :862-885).  logits [n_pos,n_cand] as written
+ *      by the two *_softmax_ce kernels (already / temperature); cand_ids [n_pos*n_cand]: per position the positive
+ *      followed by its negatives.  pred_ids / pred_probs [n_pos,n_cand] (either may be NULL): candidates sorted by
+ *      softmax probability, descending, ties to the lower candidate index (top_k order).  metrics[0] += number of
+ *      positions whose positive is in the top_n, metrics[1] += sum of 1/rank for those, metrics[2] += n_pos.       */
+int nar_rank_candidates(const float* logits, const int64_t* cand_ids, int64_t n_pos, int64_t n_cand, int32_t top_n,
+                        int64_t* pred_ids, float* pred_probs, float* metrics, void* stream);
+
 /* ---- small helpers ------------------------------------------------------------------ */
 /* out[c] += sum_r x[r,c]   (bias gradients)                                                */
 int nar_colsum_add(const float* x, int64_t rows, int64_t cols, int64_t ld, float* out, void* stream);

@@ -274,6 +274,24 @@ class NarOracle:
                 'x_in': x_in, 'x_pos': x_pos, 'x_neg': x_neg, 'e_in': e_in, 'e_pos': e_pos, 'e_neg': e_neg,
                 'rnn_out': r, 'pred': pred, 'probs': torch.softmax(logits, dim=-1)}
 
+    # ------------------------------------------------------------------ eval (ModeKeys.EVAL)
+    @staticmethod
+    def rank_and_metrics(out, labels: Dict[str, np.ndarray], negatives: np.ndarray, top_n: int):
+        """rank_items_by_predicted_prob (nar_model.py:777-795: tf.nn.top_k over all 1+K candidates = descending
+        probability, ties to the lower index) and the per-batch sums behind sparse_recall_at_top_k (:835-840) and
+        define_mrr_metric (:862-885).  -> predicted_item_ids [B,T,1+K], predicted_item_probs, hits, rr_sum, count"""
+        probs = out['probs'].detach().cpu().numpy()
+        mask = out['mask'].cpu().numpy().astype(bool)
+        ids = np.concatenate([np.asarray(labels['label_next_item'])[..., None], np.asarray(negatives)], axis=2)
+        order = np.argsort(-probs, axis=2, kind='stable')                       # top_k order
+        pred_ids = np.take_along_axis(ids, order, axis=2)
+        pred_probs = np.take_along_axis(probs, order, axis=2)
+        rank_of_pos = np.argmax(order == 0, axis=2)                             # 0-based rank of the positive
+        found = (rank_of_pos < top_n) & mask
+        hits = float(found.sum())
+        rr = float((1.0 / (rank_of_pos + 1.0))[found].sum())
+        return pred_ids, pred_probs, hits, rr, float(mask.sum())
+
     # ------------------------------------------------------------------ train
     def compute_gradients(self, out) -> Dict[str, torch.Tensor]:
         names = list(self.params.keys())

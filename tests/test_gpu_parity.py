@@ -150,3 +150,116 @@ def test_two_process_data_parallel_matches_single():
     assert abs(loss_sum[1].item() - loss_full[1].item()) / max(loss_full[1].item(), 1e-12) < 1e-5
     scale = g_full.abs().max().item()
     assert (gsum - g_full).abs().max().item() / scale < 2e-3
+
+
+def test_eval_ranking_and_metrics_vs_oracle():
+    """ModeKeys.EVAL: predicted_item_ids / probs (tf.nn.top_k order) and the HR@n / MRR@n sums against the oracle.
+    Ranks are compared where the oracle's probability gaps exceed the forward tolerance (a 1e-5 logit difference may
+    swap two near-tied candidates, which is not an error); the streaming sums must agree to within those swaps."""
+    import torch
+    from chameleon_recsys_b200.harness import make_problem, warm_state
+    from oracle import sampler_ref
+    from tools import gpu_step_check as g
+    pb = make_problem('tiny', profile='B')
+    warm_state(pb, 5)
+    hp = pb.hp
+    eng = g.make_engine(pb)
+    orc = g.make_oracle(pb, torch.float64)
+    logical = pb.layout.init_logical(7)
+    eng.set_params(logical); orc.set_params(logical)
+    it = pb.input_fn()
+    top_n = 3
+    metrics = torch.zeros(3, device='cuda')
+    tot = np.zeros(3)
+    for step in range(3):
+        f, l = it.get_next()
+        buf = pb.clicked_items_state.get_recent_clicks_buffer().copy()
+        pop = pb.clicked_items_state.get_articles_recent_pop_norm().astype(np.float32)
+        out = eng.eval_step(f, l, buf, pop, top_n=top_n, metrics=metrics, step_id=step + 1)
+        allc = np.concatenate([f['item_clicked'], l['label_last_item']], axis=1)
+        neg = sampler_ref.sample_negatives(allc, buf, hp.train_total_negative_samples, hp.train_negative_samples_from_buffer,
+                                           hp.sampler_seed, step + 1)
+        assert np.array_equal(out['negatives'].cpu().numpy(), neg)
+        o = orc.forward(f, l, neg, buf, pop)
+        ids, probs, hits, rr, cnt = orc.rank_and_metrics(o, l, neg, top_n)
+        tot += [hits, rr, cnt]
+        mask = o['mask'].cpu().numpy().astype(bool)
+        gp = out['predicted_item_probs'].cpu().numpy(); gi = out['predicted_item_ids'].cpu().numpy()
+        op, oi = probs[mask], ids[mask]                               # valid positions, session-major == engine row order
+        assert gp.shape == op.shape
+        assert np.abs(gp - op).max() < 1e-4
+        assert (np.diff(gp, axis=1) <= 0).all()                        # sorted, descending
+        gap_ok = np.ones_like(op, dtype=bool)
+        gap = np.abs(np.diff(op, axis=1)) > 1e-4
+        gap_ok[:, 1:] &= gap; gap_ok[:, :-1] &= gap                    # both neighbours clearly separated
+        assert (gi[gap_ok] == oi[gap_ok]).all()
+        assert abs(out['total_loss'] - float(o['total_loss'])) / abs(float(o['total_loss'])) < 1e-3
+    m = metrics.cpu().numpy()
+    assert m[2] == tot[2]
+    assert abs(m[0] - tot[0]) <= 1 and abs(m[1] - tot[1]) <= 0.5        # at most one near-tie swap at the top_n boundary
+
+
+def test_estimator_evaluate_roundtrip():
+    """Estimator.train then Estimator.evaluate (nar_trainer_gcom.py:511-530): EVAL shares the trained weights, returns
+    finite metrics in [0,1], leaves the weights untouched and restores ClickedItemsState (hook begin/end)."""
+    import torch
+    from chameleon_recsys_b200.estimator import build_estimator
+    from chameleon_recsys_b200.harness import make_problem, warm_state
+    pb = make_problem('tiny', profile='B')
+    warm_state(pb, 5)
+    est = build_estimator(None, pb.content_article_embeddings_matrix, pb.articles_metadata, pb.articles_features_config,
+                          pb.session_features_config, pb.hp, pb.clicked_items_state)
+    est.train(lambda: pb.input_fn(), steps=4)
+    w0 = est.model.engine.params.clone()
+    buf0 = pb.clicked_items_state.get_recent_clicks_buffer().copy()
+    res = est.evaluate(lambda: pb.input_fn(), steps=3)
+    assert set(res) >= {'loss', 'hitrate_at_n', 'mrr_at_n', 'global_step'}
+    assert np.isfinite(res['loss']) and 0.0 <= res['mrr_at_n'] <= res['hitrate_at_n'] <= 1.0
+    assert res['global_step'] == 4
+    assert torch.equal(w0, est.model.engine.params)
+    assert np.array_equal(buf0, pb.clicked_items_state.get_recent_clicks_buffer())
+    k_eval = pb.hp.eval_total_negative_samples
+    assert est._eval_spec.model.predicted_item_ids.shape[1] == 1 + k_eval
+
+
+def test_checkpoint_resume_matches_uninterrupted_run(tmp_path):
+    """train 2 + (checkpoint, fresh process state) + train 2 == train 4: weights, Adam slots, step, host state.
+    (Split-K wgrads and the embedding scatter-add accumulate with float atomics, so two runs agree to rounding.)"""
+    import torch
+    from chameleon_recsys_b200 import checkpoint as ckpt
+    from chameleon_recsys_b200.estimator import build_estimator
+    from chameleon_recsys_b200.harness import make_problem, warm_state
+
+    def fresh():
+        pb = make_problem('tiny', profile='B')
+        warm_state(pb, 5)
+        batches = []
+        it = pb.input_fn()
+        for _ in range(4):
+            batches.append(it.get_next())
+        return pb, batches
+
+    def run(pb, batches, model_dir):
+        est = build_estimator(model_dir, pb.content_article_embeddings_matrix, pb.articles_metadata,
+                              pb.articles_features_config, pb.session_features_config, pb.hp, pb.clicked_items_state)
+        est.train(lambda: iter(batches))
+        return est
+
+    pb, batches = fresh()
+    ref = run(pb, batches, None)                                       # 4 steps in one go
+    pb2, batches2 = fresh()
+    d = str(tmp_path / 'model')
+    run(pb2, batches2[:2], d)                                          # 2 steps, checkpoint written at the end
+    assert ckpt.latest_checkpoint(d).endswith('model.ckpt-2.npz')
+    pb3, batches3 = fresh()                                            # "new process": fresh weights and host state
+    est3 = run(pb3, batches3[2:], d)                                   # restores step 2, trains 2 more
+    assert est3.model.engine.global_step == 4
+    # Adam turns a +-1e-12 "zero" gradient into a +-lr update, so a few entries differ by O(lr) between ANY two runs
+    # (float atomics in split-K wgrad / scatter-add); everything else must agree to rounding, and so must the loss
+    dp = (est3.model.engine.params - ref.model.engine.params).abs()
+    assert float(dp.median()) < 1e-7 and float((dp > 1e-5).float().mean()) < 0.02, (float(dp.median()), float(dp.max()))
+    dm = (est3.model.engine.adam_m - ref.model.engine.adam_m).abs()
+    assert float(dm.max()) <= 1e-3 * float(ref.model.engine.adam_m.abs().max())
+    assert abs(est3.last_loss - ref.last_loss) / abs(ref.last_loss) < 1e-4
+    assert np.array_equal(pb3.clicked_items_state.get_recent_clicks_buffer(), pb.clicked_items_state.get_recent_clicks_buffer())
+    assert ckpt.latest_checkpoint(d).endswith('model.ckpt-4.npz')

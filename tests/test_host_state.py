@@ -94,3 +94,64 @@ def test_plan_and_layout_roundtrip():
     assert lg['main/RNN/rnn/multi_rnn_cell/cell_0/ugrnn_cell/kernel'].shape == (64 + 64, 128)
     assert np.array_equal(pbt.layout.to_logical(pbt.layout.to_internal(lg))['main/RNN/rnn/multi_rnn_cell/cell_0/ugrnn_cell/kernel'],
                           lg['main/RNN/rnn/multi_rnn_cell/cell_0/ugrnn_cell/kernel'])
+
+
+def test_checkpoint_file_roundtrip(tmp_path):
+    """checkpoint.py: logical tensors, Adam slots, step and ClickedItemsState survive save -> load -> restore; the
+    latest file is picked by step number, not by name order."""
+    from chameleon_recsys_b200 import checkpoint as ckpt
+    from chameleon_recsys_b200.clicked_items_state import ClickedItemsState
+
+    class FakeEngine:
+        def __init__(self, seed):
+            r = np.random.RandomState(seed)
+            self.sd = {'params': {'a/kernel': r.randn(3, 4).astype(np.float32), 'a/bias': r.randn(4).astype(np.float32)},
+                       'adam_m': {'a/kernel': r.randn(3, 4).astype(np.float32), 'a/bias': r.randn(4).astype(np.float32)},
+                       'adam_v': {'a/kernel': r.rand(3, 4).astype(np.float32), 'a/bias': r.rand(4).astype(np.float32)},
+                       'global_step': 7 + seed}
+
+        def state_dict(self):
+            return self.sd
+
+        def load_state_dict(self, sd):
+            self.sd = sd
+
+    st = ClickedItemsState(1.0, 50, 20, 30)
+    st.update_items_state(np.array([3, 4, 4, 9]), np.array([1000, 2000, 3000, 4000]))
+    e = FakeEngine(2)
+    d = str(tmp_path)
+    ckpt.save(ckpt.checkpoint_path(d, 9), e, st)
+    ckpt.save(ckpt.checkpoint_path(d, 10), FakeEngine(3), st)
+    assert ckpt.latest_checkpoint(d).endswith('model.ckpt-10.npz')       # 10 > 9 numerically
+    e2, st2 = FakeEngine(5), ClickedItemsState(1.0, 50, 20, 30)
+    step = ckpt.restore(ckpt.checkpoint_path(d, 9), e2, st2)
+    assert step == 9 and e2.sd['global_step'] == 9
+    for g in ('params', 'adam_m', 'adam_v'):
+        for k in e.sd[g]:
+            assert np.array_equal(e2.sd[g][k], e.sd[g][k])
+    assert np.array_equal(st2.get_recent_clicks_buffer(), st.get_recent_clicks_buffer())
+    assert np.array_equal(st2.get_articles_recent_pop_norm(), st.get_articles_recent_pop_norm())
+    assert ckpt.latest_checkpoint(str(tmp_path / 'missing')) is None
+
+
+def test_acr_resource_loaders(tmp_path):
+    """nar_utils: G1 csv + pickle and the Adressa tuple pickle; row normalisation equals sklearn's Normalizer."""
+    import pickle
+    import pandas as pd
+    from sklearn.preprocessing import Normalizer
+    from chameleon_recsys_b200 import nar_utils
+    rs = np.random.RandomState(0)
+    emb = rs.randn(6, 5).astype(np.float32); emb[0] = 0
+    df = pd.DataFrame({'article_id': np.arange(6), 'category_id': rs.randint(0, 9, 6), 'created_at_ts': rs.randint(1, 10 ** 9, 6)})
+    df.to_csv(tmp_path / 'meta.csv', index=False)
+    pickle.dump(emb, open(tmp_path / 'emb.pickle', 'wb'))
+    pickle.dump(({'category_id': {'a': 1}}, df, emb), open(tmp_path / 'acr.pickle', 'wb'))
+    d2, e2 = nar_utils.load_acr_module_resources(str(tmp_path / 'meta.csv'), str(tmp_path / 'emb.pickle'))
+    assert np.array_equal(e2, emb) and list(d2.columns) == list(df.columns)
+    enc, d3, e3 = nar_utils.load_acr_module_resources_adressa(str(tmp_path / 'acr.pickle'))
+    assert enc == {'category_id': {'a': 1}} and np.array_equal(e3, emb) and d3.equals(df)
+    meta = nar_utils.process_articles_metadata(d2, {'category_id': {}, 'created_at_ts': {}})
+    assert meta['category_id'].dtype == np.int64 and np.array_equal(meta['created_at_ts'], df['created_at_ts'].values)
+    got = nar_utils.normalize_content_embeddings(emb, 2.0)
+    want = Normalizer(norm='l2').fit_transform(emb) * 2.0
+    assert np.allclose(got, want, atol=1e-6) and not got[0].any()

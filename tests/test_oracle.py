@@ -206,3 +206,19 @@ def test_invariants_padding_and_regulariser():
     assert float(o0.forward(f, l, neg, buf, pop)['reg_loss']) == 0.0
     # recency / novelty features live in [-1, 1] for items inside the statistics' support
     assert np.isfinite(a['x_in'].detach().numpy()).all()
+
+
+def test_rank_and_metrics_known_answer():
+    """top_k order (descending, ties to the lower index), HR@n and MRR@n on a hand-made batch."""
+    import torch
+    from oracle.nar_oracle import NarOracle
+    probs = torch.tensor([[[0.1, 0.5, 0.4], [0.4, 0.4, 0.2]],
+                          [[0.6, 0.3, 0.1], [0.2, 0.3, 0.5]]], dtype=torch.float64)
+    mask = torch.tensor([[True, True], [True, False]])
+    labels = {'label_next_item': np.array([[7, 8], [9, 0]])}
+    negatives = np.array([[[1, 2], [3, 4]], [[5, 6], [0, 0]]])
+    ids, pr, hits, rr, cnt = NarOracle.rank_and_metrics({'probs': probs, 'mask': mask}, labels, negatives, top_n=2)
+    assert ids[0, 0].tolist() == [1, 2, 7] and ids[0, 1].tolist() == [8, 3, 4] and ids[1, 0].tolist() == [9, 5, 6]
+    assert np.allclose(pr[0, 0], [0.5, 0.4, 0.1])
+    # positive ranks (0-based): 2, 0, 0 over the three valid positions -> two hits at n=2, rr = 1 + 1
+    assert (hits, rr, cnt) == (2.0, 2.0, 3.0)

@@ -95,6 +95,8 @@ class NarEngine:
         self._side = None
         self._prep_flip = 0
         self.use_side_stream = os.environ.get('NAR_SIDE_STREAM', '1') == '1'
+        self._aux = None
+        self.use_aux_stream = os.environ.get('NAR_AUX_STREAM', '1') == '1'
         self._views: dict = {}
         self.last: Dict[str, torch.Tensor] = {}
         self.ops = ops
@@ -296,6 +298,37 @@ class NarEngine:
         ops.gemm(X, dY, dW, n_in, n_out, rows, a_kmajor=False, b_kmajor=False, accumulate=True,
                  split_k=0, precision=self.bwd_prec)      # 0 = library picks the split (about two waves of CTAs)
 
+    def _on_aux(self, *calls):
+        """Weight / bias gradients are only needed by Adam, so they leave the critical path: each group is launched on
+        an auxiliary stream behind an event recorded where its inputs became final, while the main stream continues
+        with the dgrad chain.  Small wgrads (a handful of CTAs each) and the column sums then overlap the main
+        stream's kernels instead of serialising with them.  Inputs of a deferred group are never overwritten later in
+        the step (the in-place dgrads of the single-stream version write to their own buffers here)."""
+        if not self.use_aux_stream:
+            for fn in calls:
+                fn()
+            return
+        if self._aux is None:
+            self._aux = torch.cuda.Stream(device=self.dev)
+            self._aux_events = [torch.cuda.Event() for _ in range(32)]       # reused round-robin: no per-step creation
+            self._aux_ev_i = 0
+        ev = self._aux_events[self._aux_ev_i]
+        self._aux_ev_i = (self._aux_ev_i + 1) % len(self._aux_events)
+        ev.record()
+        self._aux.wait_event(ev)
+        with ops.on_stream(self._aux):                # only libnar launches inside: no torch op runs on the aux stream
+            for fn in calls:
+                fn()
+        self._aux_dirty = True
+
+    def _join_aux(self):
+        if self.use_aux_stream and self._aux is not None and getattr(self, '_aux_dirty', False):
+            ev = self._aux_events[self._aux_ev_i]
+            self._aux_ev_i = (self._aux_ev_i + 1) % len(self._aux_events)
+            ev.record(self._aux)
+            torch.cuda.current_stream().wait_event(ev)
+            self._aux_dirty = False
+
     def _bgrad(self, dY, bkey, rows, cols):
         ops.colsum_add(dY, rows, cols, dY.stride(0), self.view(bkey, self.grads).view(-1))
 
@@ -344,6 +377,10 @@ class NarEngine:
 
     def step(self, st: dict, train: bool = True, keep: bool = False) -> dict:
         """Run one step on staged inputs.  Returns device tensors (loss parts, logits, negatives)."""
+        with ops.on_stream(torch.cuda.current_stream()):      # one stream lookup per step instead of one per launch
+            return self._step(st, train, keep)
+
+    def _step(self, st: dict, train: bool, keep: bool) -> dict:
         t = st['t']
         B, Bg, T, L, s0 = st['B'], st['Bg'], st['T'], st['L'], st['s0']
         K, C_, Hp, Fp = self.K, self.C, self.Hp, self.plan.Fp
@@ -421,48 +458,54 @@ class NarEngine:
         if not train:
             return out
         # =================================================================== backward
+        inplace = not self.use_aux_stream          # single-stream version reuses H1 / X / PD for their gradients
         if self.ranking == 'mlp':
             dZ2 = self._buf('dZ2', Rc, 64, cap_rows=Rcmax); dZ1 = self._buf('dZ1', Rc, 128, cap_rows=Rcmax)
-            self._wgrad(Z2, dZ3, 'M3', Rc); self._bgrad(dZ3, 'c3', Rc, 32)
+            self._on_aux(lambda: self._wgrad(Z2, dZ3, 'M3', Rc), lambda: self._bgrad(dZ3, 'c3', Rc, 32))
             self._dgrad(dZ3, 'M3', dZ2, Rc, dact=ACT_LEAKY, aux=Z2)
-            self._wgrad(Z1, dZ2, 'M2', Rc); self._bgrad(dZ2, 'c2', Rc, 64)
+            self._on_aux(lambda: self._wgrad(Z1, dZ2, 'M2', Rc), lambda: self._bgrad(dZ2, 'c2', Rc, 64))
             self._dgrad(dZ2, 'M2', dZ1, Rc, dact=ACT_LEAKY, aux=Z1)
-            self._wgrad(PD, dZ1, 'M1', Rc); self._bgrad(dZ1, 'c1', Rc, 128)
-            self._dgrad(dZ1, 'M1', PD, Rc)                       # d(prod) over PD in place (wgrad was issued first)
-            ops.mul_pred_bwd(PD, Ec, PR, L, n_cand, C_, dE[L:], dPR, cand_act=ACT_TANH)   # candidate rows: through the CAR tanh
+            self._on_aux(lambda: self._wgrad(PD, dZ1, 'M1', Rc), lambda: self._bgrad(dZ1, 'c1', Rc, 128))
+            dPD = PD if inplace else self._buf('dPD', Rc, C_, cap_rows=Rcmax)
+            self._dgrad(dZ1, 'M1', dPD, Rc)                      # d(prod); over PD in place when the wgrad is stream-ordered
+            ops.mul_pred_bwd(dPD, Ec, PR, L, n_cand, C_, dE[L:], dPR, cand_act=ACT_TANH)   # candidate rows: through the CAR tanh
         else:
             ops.act_bwd(dE[L:], Ec, Rc * C_, ACT_TANH, dE[L:])
         # FC2 / FC1 (nar_model.py:410-426)
         ops.act_bwd(dPR, PR, L * C_, ACT_TANH, dPR)
-        self._wgrad(F1, dPR, 'W4', L); self._bgrad(dPR, 'b4', L, C_)
+        self._on_aux(lambda: self._wgrad(F1, dPR, 'W4', L), lambda: self._bgrad(dPR, 'b4', L, C_))
         dF1 = self._buf('dF1', L, 512, cap_rows=Lmax)
         self._dgrad(dPR, 'W4', dF1, L, dact=ACT_LEAKY, aux=F1)
-        self._wgrad(HO[-1], dF1, 'W3', L); self._bgrad(dF1, 'b3', L, 512)
+        ho_last = HO[-1]
+        self._on_aux(lambda: self._wgrad(ho_last, dF1, 'W3', L), lambda: self._bgrad(dF1, 'b3', L, 512))
         dHO = self._buf('dHO', L, Hp, cap_rows=Lmax)
         self._dgrad(dF1, 'W3', dHO, L)
         # RNN BPTT
         for i in reversed(range(self.layers)):
             Wh = self.view('rnn%d/Wh' % i)
             ops.transpose(Wh, Hp, 2 * Hp, 2 * Hp, self.WhT[i], Hp)
-            dGX = self._buf('dGX', L, 2 * Hp, cap_rows=Lmax); HPV = self._buf('HPV', L, Hp, cap_rows=Lmax)
+            dGX = self._buf('dGX%d' % i, L, 2 * Hp, cap_rows=Lmax); HPV = self._buf('HPV%d' % i, L, Hp, cap_rows=Lmax)
             ops.ugrnn_bwd(dHO, HO[i], GT[i], CD[i], self.WhT[i], t['sess_off'], B, Hp, dGX, HPV)
             x_in = E if i == 0 else HO[i - 1]
-            self._wgrad(x_in, dGX, 'rnn%d/Wx' % i, L)
-            self._wgrad(HPV, dGX, 'rnn%d/Wh' % i, L)
-            self._bgrad(dGX, 'rnn%d/b' % i, L, 2 * Hp)
+            self._on_aux(lambda x_in=x_in, dGX=dGX, i=i: self._wgrad(x_in, dGX, 'rnn%d/Wx' % i, L),
+                         lambda HPV=HPV, dGX=dGX, i=i: self._wgrad(HPV, dGX, 'rnn%d/Wh' % i, L),
+                         lambda dGX=dGX, i=i: self._bgrad(dGX, 'rnn%d/b' % i, L, 2 * Hp))
             if i == 0:
                 self._dgrad(dGX, 'rnn0/Wx', dE, L, dact=ACT_TANH, aux=E)      # input rows of dE (pre-tanh)
             else:
-                dprev = self._buf('dHO_b', L, Hp, cap_rows=Lmax)
+                dprev = self._buf('dHO_b%d' % i, L, Hp, cap_rows=Lmax)
                 self._dgrad(dGX, 'rnn%d/Wx' % i, dprev, L)
                 dHO = dprev
         # CAR (shared weights: inputs + positives + negatives in one GEMM)
-        self._wgrad(H1, dE, 'W2', R); self._bgrad(dE, 'b2', R, C_)
-        self._dgrad(dE, 'W2', H1, R, dact=ACT_LEAKY, aux=H1)       # dH1(pre) over H1 in place
-        self._wgrad(X, H1, 'W1', R); self._bgrad(H1, 'b1', R, C_)
-        self._dgrad(H1, 'W1', X, R)                                 # dX over X in place
-        ops.gather_features_bwd(planc, row_pos, row_item, R, L, n_cand, t['event_ts'], t['max_ts'], X,
+        self._on_aux(lambda: self._wgrad(H1, dE, 'W2', R), lambda: self._bgrad(dE, 'b2', R, C_))
+        dH1 = H1 if inplace else self._buf('dH1', R, C_, cap_rows=Rmax)
+        self._dgrad(dE, 'W2', dH1, R, dact=ACT_LEAKY, aux=H1)      # dH1(pre); over H1 in place when stream-ordered
+        self._on_aux(lambda: self._wgrad(X, dH1, 'W1', R), lambda: self._bgrad(dH1, 'b1', R, C_))
+        dX = X if inplace else self._buf('dX', R, Fp, cap_rows=Rmax)
+        self._dgrad(dH1, 'W1', dX, R)                               # dX; over X in place when stream-ordered
+        ops.gather_features_bwd(planc, row_pos, row_item, R, L, n_cand, t['event_ts'], t['max_ts'], dX,
                                 self.view('gamma', self.grads).view(-1), self.view('beta', self.grads).view(-1))
+        self._join_aux()
         return out
 
     def apply_gradients(self):

@@ -22,7 +22,32 @@ def context(device: Optional[int] = None) -> Context:
     return _ctx[device]
 
 
+_STREAM_OVERRIDE: Optional[int] = None      # raw cudaStream_t the wrappers launch on instead of torch's current stream
+
+
+class on_stream:
+    """``with ops.on_stream(s):`` - every wrapper launches on ``s`` (a torch.cuda.Stream) without touching torch's
+    current-stream state (entering ``torch.cuda.stream`` costs ~10 us of host time; the engine switches streams a
+    dozen times per step).  Only libnar_b200 launches are redirected - torch ops keep using the current stream."""
+
+    def __init__(self, stream: torch.cuda.Stream):
+        self.h = stream.cuda_stream
+
+    def __enter__(self):
+        global _STREAM_OVERRIDE
+        self.prev = _STREAM_OVERRIDE
+        _STREAM_OVERRIDE = self.h
+        return self
+
+    def __exit__(self, *exc):
+        global _STREAM_OVERRIDE
+        _STREAM_OVERRIDE = self.prev
+        return False
+
+
 def _stream() -> C.c_void_p:
+    if _STREAM_OVERRIDE is not None:
+        return C.c_void_p(_STREAM_OVERRIDE)
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

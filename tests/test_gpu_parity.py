@@ -223,8 +223,9 @@ def test_estimator_evaluate_roundtrip():
 
 
 def test_checkpoint_resume_matches_uninterrupted_run(tmp_path):
-    """train 2 + (checkpoint, fresh process state) + train 2 == train 4: weights, Adam slots, step, host state.
-    (Split-K wgrads and the embedding scatter-add accumulate with float atomics, so two runs agree to rounding.)"""
+    """A checkpoint restores weights, TF-Adam slots, step and host state EXACTLY; training on from it tracks the run
+    that was never interrupted (to float-atomics noise: Adam turns a +-1e-12 "zero" gradient into a +-lr update, so
+    single entries differ by O(lr) between ANY two runs)."""
     import torch
     from chameleon_recsys_b200 import checkpoint as ckpt
     from chameleon_recsys_b200.estimator import build_estimator
@@ -233,33 +234,70 @@ def test_checkpoint_resume_matches_uninterrupted_run(tmp_path):
     def fresh():
         pb = make_problem('tiny', profile='B')
         warm_state(pb, 5)
-        batches = []
         it = pb.input_fn()
-        for _ in range(4):
-            batches.append(it.get_next())
-        return pb, batches
+        return pb, [it.get_next() for _ in range(4)]
 
-    def run(pb, batches, model_dir):
-        est = build_estimator(model_dir, pb.content_article_embeddings_matrix, pb.articles_metadata,
-                              pb.articles_features_config, pb.session_features_config, pb.hp, pb.clicked_items_state)
-        est.train(lambda: iter(batches))
-        return est
+    def estimator(pb, model_dir):
+        return build_estimator(model_dir, pb.content_article_embeddings_matrix, pb.articles_metadata,
+                               pb.articles_features_config, pb.session_features_config, pb.hp, pb.clicked_items_state)
 
-    pb, batches = fresh()
-    ref = run(pb, batches, None)                                       # 4 steps in one go
-    pb2, batches2 = fresh()
     d = str(tmp_path / 'model')
-    run(pb2, batches2[:2], d)                                          # 2 steps, checkpoint written at the end
+    pb_a, batches = fresh()
+    est_a = estimator(pb_a, d)
+    est_a.train(lambda: iter(batches[:2]))                              # 2 steps, checkpoint written at the end
     assert ckpt.latest_checkpoint(d).endswith('model.ckpt-2.npz')
-    pb3, batches3 = fresh()                                            # "new process": fresh weights and host state
-    est3 = run(pb3, batches3[2:], d)                                   # restores step 2, trains 2 more
-    assert est3.model.engine.global_step == 4
-    # Adam turns a +-1e-12 "zero" gradient into a +-lr update, so a few entries differ by O(lr) between ANY two runs
-    # (float atomics in split-K wgrad / scatter-add); everything else must agree to rounding, and so must the loss
-    dp = (est3.model.engine.params - ref.model.engine.params).abs()
-    assert float(dp.median()) < 1e-7 and float((dp > 1e-5).float().mean()) < 0.02, (float(dp.median()), float(dp.max()))
-    dm = (est3.model.engine.adam_m - ref.model.engine.adam_m).abs()
-    assert float(dm.max()) <= 1e-3 * float(ref.model.engine.adam_m.abs().max())
-    assert abs(est3.last_loss - ref.last_loss) / abs(ref.last_loss) < 1e-4
-    assert np.array_equal(pb3.clicked_items_state.get_recent_clicks_buffer(), pb.clicked_items_state.get_recent_clicks_buffer())
+    pb_b, batches_b = fresh()                                           # "new process": fresh weights and host state
+    est_b = estimator(pb_b, d)
+    est_b._ensure_spec(*batches_b[2])                                   # builds the model and restores model.ckpt-2
+    ea, eb = est_a.model.engine, est_b.model.engine
+    assert eb.global_step == 2
+    assert torch.equal(ea.params, eb.params) and torch.equal(ea.adam_m, eb.adam_m) and torch.equal(ea.adam_v, eb.adam_v)
+    assert torch.equal(ea.params_lo, eb.params_lo)
+    sa, sb = pb_a.clicked_items_state, pb_b.clicked_items_state
+    assert np.array_equal(sa.get_recent_clicks_buffer(), sb.get_recent_clicks_buffer())
+    assert np.array_equal(sa.get_articles_recent_pop_norm(), sb.get_articles_recent_pop_norm())
+    assert np.array_equal(sa.get_articles_pop(), sb.get_articles_pop())
+    est_a.train(lambda: iter(batches[2:]))                              # the uninterrupted run goes on
+    est_b.train(lambda: iter(batches_b[2:]))                            # the restored one too
+    assert eb.global_step == 4 and ea.global_step == 4
+    assert abs(est_b.last_loss - est_a.last_loss) / abs(est_a.last_loss) < 1e-3
+    dp = (ea.params - eb.params).abs()
+    assert float(dp.median()) < 1e-6
+    assert np.array_equal(sa.get_recent_clicks_buffer(), sb.get_recent_clicks_buffer())
     assert ckpt.latest_checkpoint(d).endswith('model.ckpt-4.npz')
+
+
+def test_aux_stream_gradients_match_single_stream():
+    """Weight / bias gradients computed on the auxiliary stream (engine._on_aux) equal the single-stream ones: any
+    missing event or reused buffer would show up as a difference far above the float-atomics noise."""
+    import torch
+    from chameleon_recsys_b200.harness import make_problem, warm_state
+    from tools import gpu_step_check as g
+    pb = make_problem('g1', profile='B', batch_size=64)
+    warm_state(pb, 10)
+    it = pb.input_fn()
+    batches = []
+    for _ in range(3):
+        f, l = it.get_next()
+        batches.append((f, l, pb.clicked_items_state.get_recent_clicks_buffer().copy(),
+                        pb.clicked_items_state.get_articles_recent_pop_norm().astype(np.float32)))
+    logical = pb.layout.init_logical(3)
+    grads = {}
+    for aux in (False, True):
+        eng = g.make_engine(pb)
+        eng.use_aux_stream = aux
+        eng.set_params(logical)
+        outs = []
+        for rep in range(2):                                            # twice: races are not deterministic
+            for f, l, buf, pop in batches:
+                st = eng.stage(f, l, buf, pop)
+                eng.grads.zero_()
+                eng.step(st, train=True)
+                torch.cuda.synchronize()
+                outs.append(eng.grads.clone())
+        grads[aux] = outs
+    for a, b in zip(grads[False], grads[True]):
+        scale = float(a.abs().max())
+        assert float((a - b).abs().max()) <= 2e-5 * scale, (float((a - b).abs().max()), scale)
+    for i in range(3):                                                  # and run to run
+        assert float((grads[True][i] - grads[True][i + 3]).abs().max()) <= 2e-5 * float(grads[True][i].abs().max())

@@ -77,9 +77,100 @@ class ClickedItemsState:
 
     # -- update (clicked_items_state.py:187-250)
     def update_items_state(self, batch_clicked_items, batch_clicked_timestamps):
+        """One call per step.  Runs the single-pass C implementation in libnar_b200 (``nar_host_state_update``, host
+        code) when the library is built - the numpy restatement below is the specification it is tested against
+        (tests/test_host_state.py) and costs ~0.8 ms per G1 step, which made the end-to-end loop host bound."""
+        if self._native_update(batch_clicked_items, batch_clicked_timestamps):
+            return
+        self.update_items_state_numpy(batch_clicked_items, batch_clicked_timestamps)
+
+    def update_items_state_numpy(self, batch_clicked_items, batch_clicked_timestamps):
         self._update_recently_clicked_items_buffer(batch_clicked_items, batch_clicked_timestamps)
         self._update_recent_pop_items()
         self._update_pop_items(batch_clicked_items)
+
+    _lib = None           # class-level cache: ctypes handle, or False when the library is not available
+
+    @classmethod
+    def _native(cls):
+        if cls._lib is None:
+            try:
+                from . import _lib as nl
+                cls._lib = nl.load()
+            except Exception:  # noqa: BLE001  (library not built: the numpy path is complete)
+                cls._lib = False
+        return cls._lib
+
+    def update_from_batch(self, clicked_items, clicked_timestamps, last_item_label):
+        """ItemsStateUpdaterHook.after_run in one call: ``batch_clicks_for_state_update`` + ``update_items_state``
+        (both stay as the numpy specification; the C path does the same in one pass over the padded batch)."""
+        lib = self._native()
+        ci = np.ascontiguousarray(clicked_items, dtype=np.int64)
+        if lib is False or ci.ndim != 2:
+            items, ts = batch_clicks_for_state_update(clicked_items, clicked_timestamps, last_item_label)
+            if items.size:
+                self.update_items_state(items, ts)
+            return
+        ct = np.ascontiguousarray(clicked_timestamps, dtype=np.int64)
+        ll = np.ascontiguousarray(last_item_label, dtype=np.int64).reshape(-1)
+        B, T = ci.shape
+        bs = getattr(self, '_batch_scratch', None)
+        if bs is None or bs.size < 2 * B * (T + 1):
+            bs = self._batch_scratch = np.empty(2 * B * (T + 1), dtype=np.int64)
+        ok = self._native_call(lambda buf, scratch, recent, norm, pop, hours_ms: lib.nar_host_state_update_batch(
+            buf.ctypes.data, buf.shape[0], ci.ctypes.data, ct.ctypes.data, ll.ctypes.data, B, T, hours_ms, bs.ctypes.data,
+            scratch.ctypes.data, recent.ctypes.data, norm.ctypes.data, pop.ctypes.data, self.num_items,
+            1.0 / self.recent_clicks_for_normalization), keep_pop_on_empty=not (ci.any() or ll.any()))
+        if not ok:                            # unusual array layout: the numpy specification handles everything
+            items, ts = batch_clicks_for_state_update(clicked_items, clicked_timestamps, last_item_label)
+            if items.size:
+                self.update_items_state_numpy(items, ts)
+
+    def _native_update(self, batch_clicked_items, batch_clicked_timestamps) -> bool:
+        lib = self._native()
+        if lib is False:
+            return False
+        items = np.ascontiguousarray(batch_clicked_items, dtype=np.int64).reshape(-1)
+        ts = np.ascontiguousarray(batch_clicked_timestamps, dtype=np.int64).reshape(-1)
+        if items.size == 0 or items.size != ts.size:
+            return False
+        return self._native_call(lambda buf, scratch, recent, norm, pop, hours_ms: lib.nar_host_state_update(
+            buf.ctypes.data, buf.shape[0], items.ctypes.data, ts.ctypes.data, items.size, hours_ms, scratch.ctypes.data,
+            recent.ctypes.data, norm.ctypes.data, pop.ctypes.data, self.num_items,
+            1.0 / self.recent_clicks_for_normalization))
+
+    def _native_call(self, fn, keep_pop_on_empty: bool = False) -> bool:
+        if keep_pop_on_empty:
+            return True                       # nothing but padding in the batch: the hook does not touch the state
+        buf = self.pop_recent_clicks_buffer
+        if buf.dtype != np.int64 or not buf.flags['C_CONTIGUOUS'] or not buf.flags['WRITEABLE'] or \
+                buf.shape != (self.recent_clicks_buffer_max_size, 2):
+            buf = np.ascontiguousarray(buf, dtype=np.int64).copy()
+            if buf.shape != (self.recent_clicks_buffer_max_size, 2):
+                return False
+        scratch = getattr(self, '_scratch', None)
+        if scratch is None or scratch.shape != buf.shape:
+            scratch = self._scratch = np.empty_like(buf)
+        # two alternating output sets: fresh 368 KB arrays per step cost more (page faults) than the update itself, and
+        # whoever still holds the previous step's arrays (a feed dict) keeps seeing that step's values
+        flip = self._flip = 1 - getattr(self, '_flip', 0)
+        outs = getattr(self, '_outs', None)
+        if outs is None or outs[0][0].size != self.num_items:
+            outs = self._outs = [(np.empty(self.num_items, dtype=np.int64), np.empty(self.num_items, dtype=np.float64))
+                                 for _ in range(2)]
+        recent, norm = outs[flip]
+        pop = self.articles_pop
+        if pop.dtype != np.int64 or not pop.flags['C_CONTIGUOUS'] or not pop.flags['WRITEABLE']:
+            pop = np.ascontiguousarray(pop, dtype=np.int64).copy()
+        hours_ms = int(self.recent_clicks_buffer_hours * 1000 * 60 * 60)
+        rc = fn(buf, scratch, recent, norm, pop, hours_ms)
+        if rc != 0:
+            raise ValueError('nar_host_state_update failed (%d): article id outside [0, num_items)?' % rc)
+        self.pop_recent_clicks_buffer = buf
+        self.articles_recent_pop = recent
+        self.articles_recent_pop_norm = norm
+        self.articles_pop = pop
+        return True
 
     def _update_recently_clicked_items_buffer(self, batch_clicked_items, batch_clicked_timestamps):
         batch = np.hstack([np.asarray(batch_clicked_items, dtype=np.int64).reshape(-1, 1),

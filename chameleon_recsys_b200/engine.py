@@ -88,6 +88,8 @@ class NarEngine:
         self.stats = torch.zeros(24, device=d)
         self.loss_dev = torch.zeros(4, device=d)          # [xe_sum, reg, -, -]
         self.loss_host = torch.zeros(4).pin_memory()
+        self._loss_hosts = [self.loss_host, torch.zeros(4).pin_memory()]    # two in flight: submit(n+1) before result(n)
+        self._loss_slot = 0
         self._bufs: Dict[str, torch.Tensor] = {}
         self._pinned: Dict[str, torch.Tensor] = {}
         self._sampler_ws = None
@@ -97,6 +99,8 @@ class NarEngine:
         self.use_side_stream = os.environ.get('NAR_SIDE_STREAM', '1') == '1'
         self._aux = None
         self.use_aux_stream = os.environ.get('NAR_AUX_STREAM', '1') == '1'
+        self.split_fwd = os.environ.get('NAR_SPLIT_FWD', '1') == '1'     # session branch under the candidate CAR GEMMs
+        self.split_bwd = os.environ.get('NAR_SPLIT_BWD', '0') == '1'     # measured slower (1.77 vs 1.63 ms): off
         self._views: dict = {}
         self.last: Dict[str, torch.Tensor] = {}
         self.ops = ops
@@ -298,7 +302,7 @@ class NarEngine:
         ops.gemm(X, dY, dW, n_in, n_out, rows, a_kmajor=False, b_kmajor=False, accumulate=True,
                  split_k=0, precision=self.bwd_prec)      # 0 = library picks the split (about two waves of CTAs)
 
-    def _on_aux(self, *calls):
+    def _on_aux(self, *calls, done_event: bool = False):
         """Weight / bias gradients are only needed by Adam, so they leave the critical path: each group is launched on
         an auxiliary stream behind an event recorded where its inputs became final, while the main stream continues
         with the dgrad chain.  Small wgrads (a handful of CTAs each) and the column sums then overlap the main
@@ -307,7 +311,7 @@ class NarEngine:
         if not self.use_aux_stream:
             for fn in calls:
                 fn()
-            return
+            return None
         if self._aux is None:
             self._aux = torch.cuda.Stream(device=self.dev)
             self._aux_events = [torch.cuda.Event() for _ in range(32)]       # reused round-robin: no per-step creation
@@ -320,6 +324,12 @@ class NarEngine:
             for fn in calls:
                 fn()
         self._aux_dirty = True
+        if done_event:                                # lets the main stream wait for THIS group, not the whole queue
+            dev = self._aux_events[self._aux_ev_i]
+            self._aux_ev_i = (self._aux_ev_i + 1) % len(self._aux_events)
+            dev.record(self._aux)
+            return dev
+        return None
 
     def _join_aux(self):
         if self.use_aux_stream and self._aux is not None and getattr(self, '_aux_dirty', False):
@@ -409,23 +419,37 @@ class NarEngine:
         # ---- CAR (nar_model.py:374-405)
         H1 = self._buf('H1', R, C_, cap_rows=Rmax)
         E = self._buf('E', R, C_, cap_rows=Rmax)
-        self._fwd(X, 'W1', 'b1', H1, R, ACT_LEAKY)
-        self._fwd(H1, 'W2', 'b2', E, R, ACT_TANH)
-        # ---- RNN (nar_model.py:408, :1308-1342)
-        rnn_in = E
         HO, GT, CD, GX = [], [], [], []
-        for i in range(self.layers):
-            gx = self._buf('GX%d' % i, L, 2 * Hp, cap_rows=Lmax)
-            ho = self._buf('HO%d' % i, L, Hp, cap_rows=Lmax); gt = self._buf('GT%d' % i, L, Hp, cap_rows=Lmax); cd = self._buf('CD%d' % i, L, Hp, cap_rows=Lmax)
-            self._fwd(rnn_in, 'rnn%d/Wx' % i, 'rnn%d/b' % i, gx, L, ACT_NONE)
-            ops.ugrnn_fwd(gx, self.view('rnn%d/Wh' % i), t['sess_off'], B, Hp, ho, gt, cd)
-            HO.append(ho); GT.append(gt); CD.append(cd); GX.append(gx)
-            rnn_in = ho
-        # ---- session representation (nar_model.py:410-438)
         F1 = self._buf('F1', L, 512, cap_rows=Lmax)
         PR = self._buf('PR', L, C_, cap_rows=Lmax)
-        self._fwd(HO[-1], 'W3', 'b3', F1, L, ACT_LEAKY)
-        self._fwd(F1, 'W4', 'b4', PR, L, ACT_TANH)
+        for i in range(self.layers):
+            GX.append(self._buf('GX%d' % i, L, 2 * Hp, cap_rows=Lmax))
+            HO.append(self._buf('HO%d' % i, L, Hp, cap_rows=Lmax)); GT.append(self._buf('GT%d' % i, L, Hp, cap_rows=Lmax))
+            CD.append(self._buf('CD%d' % i, L, Hp, cap_rows=Lmax))
+
+        def session_branch():
+            # ---- RNN (nar_model.py:408, :1308-1342) and session representation (:410-438): rows [0, L) only
+            rnn_in = E
+            for i in range(self.layers):
+                self._fwd(rnn_in, 'rnn%d/Wx' % i, 'rnn%d/b' % i, GX[i], L, ACT_NONE)
+                ops.ugrnn_fwd(GX[i], self.view('rnn%d/Wh' % i), t['sess_off'], B, Hp, HO[i], GT[i], CD[i])
+                rnn_in = HO[i]
+            self._fwd(HO[-1], 'W3', 'b3', F1, L, ACT_LEAKY)
+            self._fwd(F1, 'W4', 'b4', PR, L, ACT_TANH)
+
+        if self.use_aux_stream and self.split_fwd and Rc > 0:
+            # The session branch (a chain of small kernels on L rows) only needs the CAR embeddings of the INPUT rows:
+            # those go first, then the branch runs on the auxiliary stream under the big CAR GEMMs of the candidate rows.
+            self._fwd(X[:L], 'W1', 'b1', H1[:L], L, ACT_LEAKY)
+            self._fwd(H1[:L], 'W2', 'b2', E[:L], L, ACT_TANH)
+            self._on_aux(session_branch)
+            self._fwd(X[L:], 'W1', 'b1', H1[L:], Rc, ACT_LEAKY)
+            self._fwd(H1[L:], 'W2', 'b2', E[L:], Rc, ACT_TANH)
+            self._join_aux()
+        else:
+            self._fwd(X, 'W1', 'b1', H1, R, ACT_LEAKY)
+            self._fwd(H1, 'W2', 'b2', E, R, ACT_TANH)
+            session_branch()
         # ---- scorer + loss (nar_model.py:444-517, :639-667)
         Ec = E[L:]
         logits = self._buf('logits', L, n_cand, cap_rows=Lmax)
@@ -471,38 +495,58 @@ class NarEngine:
             ops.mul_pred_bwd(dPD, Ec, PR, L, n_cand, C_, dE[L:], dPR, cand_act=ACT_TANH)   # candidate rows: through the CAR tanh
         else:
             ops.act_bwd(dE[L:], Ec, Rc * C_, ACT_TANH, dE[L:])
-        # FC2 / FC1 (nar_model.py:410-426)
-        ops.act_bwd(dPR, PR, L * C_, ACT_TANH, dPR)
-        self._on_aux(lambda: self._wgrad(F1, dPR, 'W4', L), lambda: self._bgrad(dPR, 'b4', L, C_))
-        dF1 = self._buf('dF1', L, 512, cap_rows=Lmax)
-        self._dgrad(dPR, 'W4', dF1, L, dact=ACT_LEAKY, aux=F1)
-        ho_last = HO[-1]
-        self._on_aux(lambda: self._wgrad(ho_last, dF1, 'W3', L), lambda: self._bgrad(dF1, 'b3', L, 512))
-        dHO = self._buf('dHO', L, Hp, cap_rows=Lmax)
-        self._dgrad(dF1, 'W3', dHO, L)
-        # RNN BPTT
-        for i in reversed(range(self.layers)):
-            Wh = self.view('rnn%d/Wh' % i)
-            ops.transpose(Wh, Hp, 2 * Hp, 2 * Hp, self.WhT[i], Hp)
-            dGX = self._buf('dGX%d' % i, L, 2 * Hp, cap_rows=Lmax); HPV = self._buf('HPV%d' % i, L, Hp, cap_rows=Lmax)
-            ops.ugrnn_bwd(dHO, HO[i], GT[i], CD[i], self.WhT[i], t['sess_off'], B, Hp, dGX, HPV)
-            x_in = E if i == 0 else HO[i - 1]
-            self._on_aux(lambda x_in=x_in, dGX=dGX, i=i: self._wgrad(x_in, dGX, 'rnn%d/Wx' % i, L),
+        dH1 = H1 if inplace else self._buf('dH1', R, C_, cap_rows=Rmax)
+        dX = X if inplace else self._buf('dX', R, Fp, cap_rows=Rmax)
+
+        def session_backward(deferred):
+            """FC2 / FC1 (nar_model.py:410-426) -> BPTT -> d(E) of the input rows.  ``deferred(*calls)`` runs the weight /
+            bias gradients: on the auxiliary stream (single-branch schedule) or inline (when this whole branch already
+            runs there)."""
+            ops.act_bwd(dPR, PR, L * C_, ACT_TANH, dPR)
+            deferred(lambda: self._wgrad(F1, dPR, 'W4', L), lambda: self._bgrad(dPR, 'b4', L, C_))
+            dF1 = self._buf('dF1', L, 512, cap_rows=Lmax)
+            self._dgrad(dPR, 'W4', dF1, L, dact=ACT_LEAKY, aux=F1)
+            ho_last = HO[-1]
+            deferred(lambda: self._wgrad(ho_last, dF1, 'W3', L), lambda: self._bgrad(dF1, 'b3', L, 512))
+            dHO = self._buf('dHO', L, Hp, cap_rows=Lmax)
+            self._dgrad(dF1, 'W3', dHO, L)
+            for i in reversed(range(self.layers)):
+                Wh = self.view('rnn%d/Wh' % i)
+                ops.transpose(Wh, Hp, 2 * Hp, 2 * Hp, self.WhT[i], Hp)
+                dGX = self._buf('dGX%d' % i, L, 2 * Hp, cap_rows=Lmax); HPV = self._buf('HPV%d' % i, L, Hp, cap_rows=Lmax)
+                ops.ugrnn_bwd(dHO, HO[i], GT[i], CD[i], self.WhT[i], t['sess_off'], B, Hp, dGX, HPV)
+                x_in = E if i == 0 else HO[i - 1]
+                deferred(lambda x_in=x_in, dGX=dGX, i=i: self._wgrad(x_in, dGX, 'rnn%d/Wx' % i, L),
                          lambda HPV=HPV, dGX=dGX, i=i: self._wgrad(HPV, dGX, 'rnn%d/Wh' % i, L),
                          lambda dGX=dGX, i=i: self._bgrad(dGX, 'rnn%d/b' % i, L, 2 * Hp))
-            if i == 0:
-                self._dgrad(dGX, 'rnn0/Wx', dE, L, dact=ACT_TANH, aux=E)      # input rows of dE (pre-tanh)
-            else:
-                dprev = self._buf('dHO_b%d' % i, L, Hp, cap_rows=Lmax)
-                self._dgrad(dGX, 'rnn%d/Wx' % i, dprev, L)
-                dHO = dprev
-        # CAR (shared weights: inputs + positives + negatives in one GEMM)
-        self._on_aux(lambda: self._wgrad(H1, dE, 'W2', R), lambda: self._bgrad(dE, 'b2', R, C_))
-        dH1 = H1 if inplace else self._buf('dH1', R, C_, cap_rows=Rmax)
-        self._dgrad(dE, 'W2', dH1, R, dact=ACT_LEAKY, aux=H1)      # dH1(pre); over H1 in place when stream-ordered
-        self._on_aux(lambda: self._wgrad(X, dH1, 'W1', R), lambda: self._bgrad(dH1, 'b1', R, C_))
-        dX = X if inplace else self._buf('dX', R, Fp, cap_rows=Rmax)
-        self._dgrad(dH1, 'W1', dX, R)                               # dX; over X in place when stream-ordered
+                if i == 0:
+                    self._dgrad(dGX, 'rnn0/Wx', dE, L, dact=ACT_TANH, aux=E)      # input rows of dE (pre-tanh)
+                else:
+                    dprev = self._buf('dHO_b%d' % i, L, Hp, cap_rows=Lmax)
+                    self._dgrad(dGX, 'rnn%d/Wx' % i, dprev, L)
+                    dHO = dprev
+
+        def car_backward(lo, n, deferred):
+            """CAR backward (shared weights) for rows [lo, lo+n)."""
+            h1, de, dh1, x, dx = H1[lo:lo + n], dE[lo:lo + n], dH1[lo:lo + n], X[lo:lo + n], dX[lo:lo + n]
+            deferred(lambda: self._wgrad(h1, de, 'W2', n), lambda: self._bgrad(de, 'b2', n, C_))
+            self._dgrad(de, 'W2', dh1, n, dact=ACT_LEAKY, aux=h1)      # dH1(pre); over H1 in place when stream-ordered
+            deferred(lambda: self._wgrad(x, dh1, 'W1', n), lambda: self._bgrad(dh1, 'b1', n, C_))
+            self._dgrad(dh1, 'W1', dx, n)                               # dX; over X in place when stream-ordered
+
+        def inline(*calls):
+            for fn in calls:
+                fn()
+
+        if self.use_aux_stream and self.split_bwd and Rc > 0:
+            # two branches: the candidate rows' CAR backward (big GEMMs, main stream) does not depend on the session
+            # branch (FC -> BPTT -> input rows' CAR backward: small kernels), which runs on the auxiliary stream
+            ev_rows = self._on_aux(lambda: session_backward(inline), lambda: car_backward(0, L, inline), done_event=True)
+            car_backward(L, Rc, self._on_aux)
+            torch.cuda.current_stream().wait_event(ev_rows)             # dX[:L] is final
+        else:
+            session_backward(self._on_aux)
+            car_backward(0, R, self._on_aux)
         ops.gather_features_bwd(planc, row_pos, row_item, R, L, n_cand, t['event_ts'], t['max_ts'], dX,
                                 self.view('gamma', self.grads).view(-1), self.view('beta', self.grads).view(-1))
         self._join_aux()
@@ -522,31 +566,40 @@ class NarEngine:
             self._side = torch.cuda.Stream(device=self.dev)
         return self._side
 
-    def stage_ahead(self, features, labels, buffer, pop_norm, slot: str) -> dict:
+    def stage_ahead(self, features, labels, buffer, pop_norm, slot: str, after: Optional[torch.cuda.Event] = None) -> dict:
         """Stage the NEXT step while the current one runs: the host packs the batch into the slot's pinned buffer; the
         H2D copy and the weight-independent front (sampler, row lists, statistics) run on a side stream next to the
         current step's GEMMs (measured on B200: 2.26 vs 2.35 ms per step).  NAR_SIDE_STREAM=0 queues the copy behind
         the running step on the main stream instead and leaves the front inline."""
         if self.use_side_stream:
             side = self.side_stream()
+            if after is not None:
+                side.wait_event(after)        # the step that last read this slot's buffers (two slots alternate) is done
             st = self.stage(features, labels, buffer, pop_norm, slot=slot, stream=side)
             return self.prepare(st, self.global_step + 1, stream=side)
         return self.stage(features, labels, buffer, pop_norm, slot=slot)
 
     def submit(self, st: dict, keep: bool = False) -> dict:
+        """Queue one training step; nothing here waits for the GPU.  ``result(out)`` later waits for THIS step only
+        (event), so the caller may queue step n+1 before reading the loss of step n - no bubble between steps."""
         self.grads.zero_()
         out = self.step(st, train=True, keep=keep)
         if st['L'] > 0 or self.world > 1:
             self.apply_gradients()
         if self.world > 1:
             torch.distributed.all_reduce(self.loss_dev, group=self.pg)
-        self.loss_host.copy_(self.loss_dev, non_blocking=True)
-        out['stage'] = st
+        self._loss_slot ^= 1
+        host = self._loss_hosts[self._loss_slot]
+        host.copy_(self.loss_dev, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+        out['stage'], out['loss_host'], out['done'] = st, host, done
         return out
 
     def result(self, out: dict) -> dict:
-        torch.cuda.current_stream().synchronize()
-        out['xe_loss'] = float(self.loss_host[0]); out['reg_loss'] = float(self.loss_host[1])
+        out['done'].synchronize()
+        host = out['loss_host']
+        out['xe_loss'] = float(host[0]); out['reg_loss'] = float(host[1])
         out['total_loss'] = out['xe_loss'] + out['reg_loss']
         return out
 

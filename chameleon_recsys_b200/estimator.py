@@ -145,7 +145,8 @@ class Estimator:
         """hook.before_run -> train_op -> hook.after_run per batch (MonitoredTrainingSession), software-pipelined:
         while the GPU runs step n, the host folds batch n into ClickedItemsState (it depends on the batch's ids only,
         nar_model.py:1635-1650), fetches batch n+1 (tf.data prefetch(1), datasets.py:142) and stages it - H2D copy,
-        negative sampling, row lists, normalisation statistics - on a side stream; then it reads the loss of step n."""
+        negative sampling, row lists, normalisation statistics - on a side stream; the loss of step n is read only after
+        step n+1 has been queued (two pinned loss slots, one event per step), so the GPU never waits for the host."""
         it = input_fn()
 
         def fetch():
@@ -170,6 +171,15 @@ class Estimator:
             h.begin()
         feed = feed_of(spec)
         st_next = eng.stage_ahead(nxt[0], nxt[1], feed['pop_recent_items_buffer'], feed['articles_recent_pop_norm'], 'pipe0')
+        pending = None                                              # (features, labels, out) of the step whose loss is unread
+
+        def finish(p):
+            f_, l_, o_ = p
+            o_ = eng.result(o_)                                     # waits for that step only (event), reads its loss
+            spec.model._publish(f_, l_, o_)
+            self.last_loss = o_.get('total_loss')
+            self.interactions += int(o_['stage']['L_global'])
+
         while nxt is not None:
             features, labels = nxt
             out = eng.submit(st_next)                               # step n queued on the main stream
@@ -181,12 +191,15 @@ class Estimator:
             nxt = fetch() if (steps is None or n < steps) else None
             if nxt is not None:
                 feed = feed_of(spec)
+                # slot (n & 1) was last read by step n-1 (= pending): its event gates the side-stream copy
                 st_next = eng.stage_ahead(nxt[0], nxt[1], feed['pop_recent_items_buffer'],
-                                          feed['articles_recent_pop_norm'], 'pipe%d' % (n & 1))
-            out = eng.result(out)                                   # D2H loss of step n (sync)
-            spec.model._publish(features, labels, out)
-            self.last_loss = out.get('total_loss')
-            self.interactions += int(out['stage']['L_global'])
+                                          feed['articles_recent_pop_norm'], 'pipe%d' % (n & 1),
+                                          after=pending[2]['done'] if pending is not None else None)
+            if pending is not None:
+                finish(pending)                                      # loss of step n-1: the GPU already runs step n
+            pending = (features, labels, out)
+        if pending is not None:
+            finish(pending)
         for h in spec.training_chief_hooks:
             h.end()
         if self.model_dir:

@@ -166,10 +166,8 @@ class ItemsStateUpdaterHook:
 
     def after_run(self, run_context, run_values: dict):
         """run_values: {'clicked_items','clicked_timestamps','last_item_label'} (nar_model.py:1505-1508)."""
-        items, ts = batch_clicks_for_state_update(run_values['clicked_items'], run_values['clicked_timestamps'],
-                                                  run_values['last_item_label'])
-        if items.size:
-            self.clicked_items_state.update_items_state(items, ts)
+        self.clicked_items_state.update_from_batch(run_values['clicked_items'], run_values['clicked_timestamps'],
+                                                   run_values['last_item_label'])
 
     def end(self, session=None):
         if self.mode == ModeKeys.EVAL:

@@ -209,6 +209,21 @@ int nar_cosine_softmax_ce(const float* cand, const float* pred, int64_t n_pos, i
 int nar_rank_candidates(const float* logits, const int64_t* cand_ids, int64_t n_pos, int64_t n_cand, int32_t top_n,
                         int64_t* pred_ids, float* pred_probs, float* metrics, void* stream);
 
+/* ---- host state (CPU, no CUDA): ClickedItemsState.update_items_state (clicked_items_state.py:187-250) in one pass.
+ *      buffer [cap,2] int64 {item, timestamp} newest first, zero padded (in/out); batch_items / batch_ts: the step's
+ *      non-padded clicks in batch order (nar_model.py:1635-1646); hours_ms = recent_clicks_buffer_hours * 3.6e6;
+ *      scratch [cap,2]; recent_pop [V] (out), pop_norm [V] float64 (out) = max(pop / (sum(pop) + 1), min_norm_pop);
+ *      articles_pop [V] (in/out, += bincount(batch)).                                                           */
+int nar_host_state_update(int64_t* buffer, int64_t cap, const int64_t* batch_items, const int64_t* batch_ts,
+                          int64_t n_batch, int64_t hours_ms, int64_t* scratch, int64_t* recent_pop,
+                          double* pop_norm, int64_t* articles_pop, int64_t num_items, double min_norm_pop);
+/* the same, straight from the padded batch (ItemsStateUpdaterHook.after_run nar_model.py:1635-1646): item_clicked /
+ * event_ts [B,T], label_last [B]; batch_scratch [2*B*(T+1)] int64                                                */
+int nar_host_state_update_batch(int64_t* buffer, int64_t cap, const int64_t* item_clicked, const int64_t* event_ts,
+                                const int64_t* label_last, int64_t B, int64_t T, int64_t hours_ms,
+                                int64_t* batch_scratch, int64_t* scratch, int64_t* recent_pop, double* pop_norm,
+                                int64_t* articles_pop, int64_t num_items, double min_norm_pop);
+
 /* ---- small helpers ------------------------------------------------------------------ */
 /* out[c] += sum_r x[r,c]   (bias gradients)                                                */
 int nar_colsum_add(const float* x, int64_t rows, int64_t cols, int64_t ld, float* out, void* stream);

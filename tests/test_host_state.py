@@ -155,3 +155,52 @@ def test_acr_resource_loaders(tmp_path):
     got = nar_utils.normalize_content_embeddings(emb, 2.0)
     want = Normalizer(norm='l2').fit_transform(emb) * 2.0
     assert np.allclose(got, want, atol=1e-6) and not got[0].any()
+
+
+def test_native_state_update_equals_numpy_spec():
+    """libnar_b200's nar_host_state_update (C, host) against the numpy restatement, step by step on a stream that
+    exercises the hour cut-off, the clip at max size, padding and repeated ids."""
+    from chameleon_recsys_b200 import _lib
+    from chameleon_recsys_b200.clicked_items_state import ClickedItemsState
+    _lib.load()                                                   # the library must be there: build() made it
+    rs = np.random.RandomState(1)
+    a = ClickedItemsState(0.5, 300, 50, 400)
+    b = ClickedItemsState(0.5, 300, 50, 400)
+    t = 1_500_000_000_000
+    for step in range(60):
+        n = int(rs.randint(1, 90))
+        items = rs.randint(1, 400, n).astype(np.int64)
+        t += int(rs.randint(0, 600_000))                         # up to 10 min between batches, 30 min window
+        ts = (t + rs.randint(-200_000, 200_000, n)).astype(np.int64)
+        a.update_items_state(items, ts)                           # native
+        b.update_items_state_numpy(items, ts)                     # spec
+        assert ClickedItemsState._lib not in (None, False)
+        assert np.array_equal(a.get_recent_clicks_buffer(), b.get_recent_clicks_buffer()), step
+        assert np.array_equal(a.pop_recent_clicks_buffer, b.pop_recent_clicks_buffer), step
+        assert np.array_equal(a.get_articles_recent_pop(), b.get_articles_recent_pop())
+        assert a.get_articles_recent_pop_norm().dtype == np.float64
+        assert np.array_equal(a.get_articles_recent_pop_norm(), b.get_articles_recent_pop_norm())   # bit-exact float64
+        assert np.array_equal(a.get_articles_pop(), b.get_articles_pop())
+    with pytest.raises(ValueError):
+        a.update_items_state(np.array([400]), np.array([t]))      # id outside [0, num_items)
+
+
+def test_native_update_from_batch_equals_hook_spec():
+    """update_from_batch (one C pass over the padded batch) == batch_clicks_for_state_update + numpy update."""
+    from chameleon_recsys_b200.clicked_items_state import ClickedItemsState
+    pb = make_problem('tiny', profile='B')
+    it = pb.input_fn()
+    a = ClickedItemsState(1.0, 400, 100, pb.plan.num_items)
+    b = ClickedItemsState(1.0, 400, 100, pb.plan.num_items)
+    for step in range(12):
+        f, l = it.get_next()
+        a.update_from_batch(f['item_clicked'], f['event_timestamp'], l['label_last_item'])
+        items, ts = batch_clicks_for_state_update(f['item_clicked'], f['event_timestamp'], l['label_last_item'])
+        b.update_items_state_numpy(items, ts)
+        assert np.array_equal(a.pop_recent_clicks_buffer, b.pop_recent_clicks_buffer), step
+        assert np.array_equal(a.get_articles_recent_pop_norm(), b.get_articles_recent_pop_norm())
+        assert np.array_equal(a.get_articles_pop(), b.get_articles_pop())
+    z = np.zeros_like(f['item_clicked'])
+    before = a.pop_recent_clicks_buffer.copy()
+    a.update_from_batch(z, z, np.zeros_like(l['label_last_item']))          # all padding: state untouched
+    assert np.array_equal(before, a.pop_recent_clicks_buffer)

@@ -14,7 +14,9 @@ HBM layout (per step; L = valid positions, n_cand = 1+K, R = L + L*n_cand rows):
   GX  [L, 2Hp]  x Wx + b per RNN layer   HO/GT/CD [L, Hp] state / gate / candidate
   F1  [L, 512]  PR [L, C] predicted embedding
   PD  [Rc, C]   cand * pred   Z1 [Rc,128] Z2 [Rc,64] Z3 [Rc,32]   logits [L, n_cand]
-Backward reuses the same buffers in place (dH1 over H1, dX over X, dprod over PD).
+Backward: with the auxiliary stream (default) the gradients dH1 / dX / dPD have their own buffers, because the weight
+gradients that read H1 / X / PD run concurrently with the dgrad chain; the single-stream schedule (NAR_AUX_STREAM=0)
+reuses the forward buffers in place (dH1 over H1, dX over X, dprod over PD).
 """
 from __future__ import annotations
 

@@ -222,3 +222,23 @@ def test_rank_and_metrics_known_answer():
     assert np.allclose(pr[0, 0], [0.5, 0.4, 0.1])
     # positive ranks (0-based): 2, 0, 0 over the three valid positions -> two hits at n=2, rr = 1 + 1
     assert (hits, rr, cnt) == (2.0, 2.0, 3.0)
+
+
+def test_eval_metrics_match_reference_metric_classes():
+    """HR@n / MRR@n streaming values of the oracle's rank_and_metrics == the reference's own HitRate / MRR classes
+    (tests/golden/metrics_golden.npz, generated by tests/golden/make_metrics_golden.py from nar/metrics.py)."""
+    import os
+    import torch
+    from oracle.nar_oracle import NarOracle
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'metrics_golden.npz'))
+    for topn in (1, 3, 5):
+        hits = rr = cnt = 0.0
+        for b in range(4):
+            probs = g['top%d/b%d/probs' % (topn, b)]
+            labels = g['top%d/b%d/labels' % (topn, b)]
+            negatives = g['top%d/b%d/negatives' % (topn, b)]
+            out = {'probs': torch.from_numpy(probs), 'mask': torch.from_numpy(labels != 0)}
+            _, _, h, r, c = NarOracle.rank_and_metrics(out, {'label_next_item': labels}, negatives, topn)
+            hits += h; rr += r; cnt += c
+            assert abs(hits / cnt - g['top%d/hitrate' % topn][b]) < 1e-12
+            assert abs(rr / cnt - g['top%d/mrr' % topn][b]) < 1e-12

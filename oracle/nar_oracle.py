@@ -8,8 +8,9 @@ parity unpinned: the reference arithmetic lives in TensorFlow 1.12.3 (requiremen
 which cannot be installed here (Python 3.12, no network), and the reference has no test,
 golden vector or fixture for logits / loss / gradients / Adam.  This
 file is therefore a line-by-line restatement of the graph, pinned only by (i) hand-derived
-known answers (tests/test_oracle_known_answers.py), (ii) finite-difference gradients,
-(iii) invariants from the code.  Every function cites the lines it follows.
+known answers (tests/test_oracle.py), (ii) finite-difference gradients, (iii) invariants from
+the code; its evaluation metrics (HR@n / MRR@n) ARE pinned to the reference's own numpy classes
+(tests/golden/make_metrics_golden.py).  Every function cites the lines it follows.
 
 Restated: nar_module/nar/nar_model.py:219-245 (inputs/masks), :730-773 (get_features),
 :887-907 (scale/centre), :921-994 (item features), :996-1039 (normalisation), :1055-1089

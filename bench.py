@@ -518,8 +518,11 @@ def main():
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3
     if args.impl == 'reference':
-        if args.steps > 10:
-            args.steps = 10          # bounded: each oracle step is ~1-3 s of CPU work
+        # bounded sample: one oracle step is ~2.5 s of CPU work per 256 sessions and the global batch grows with --gpus
+        # (weak scaling), so the step count shrinks with it: ~25 s of timed work at N=1, ~45 s at N=8
+        cap = max(2, 10 // max(1, args.gpus))
+        if args.steps > cap:
+            args.steps = cap
         args.warmup = min(args.warmup, 1)
         return run_reference(args)
     return run_ours(args)

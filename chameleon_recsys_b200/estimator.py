@@ -249,6 +249,9 @@ class Estimator:
             nxt = fetch() if (steps is None or n < steps) else None
         for h in spec.evaluation_hooks:
             h.end()
+        eng = spec.model.engine
+        if eng.world > 1:                                           # data parallel: every rank ranked its own sessions
+            torch.distributed.all_reduce(metrics, group=eng.pg)
         m = metrics.cpu().numpy()
         cnt = max(float(m[2]), 1.0)
         return {'loss': loss_sum / max(n, 1), 'hitrate_at_n': float(m[0]) / cnt, 'mrr_at_n': float(m[1]) / cnt,

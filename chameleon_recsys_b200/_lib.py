@@ -72,6 +72,7 @@ _SIGNATURES = {
     'nar_rank_candidates': (C.c_int, [vp, vp, i64, i64, i32, vp, vp, vp, vp]),
     'nar_host_state_update': (C.c_int, [vp, i64, vp, vp, i64, i64, vp, vp, vp, vp, i64, C.c_double]),
     'nar_host_state_update_batch': (C.c_int, [vp, i64, vp, vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, i64, C.c_double]),
+    'nar_state_update': (C.c_int, [vp, vp, i64, vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, i64, C.c_double, vp, vp]),
     'nar_colsum_add': (C.c_int, [vp, i64, i64, i64, vp, vp]),
     'nar_act_bwd': (C.c_int, [vp, vp, i64, C.c_int, vp, vp]),
     'nar_l2_loss_add': (C.c_int, [vp, i64, f32, vp, vp]),

@@ -224,6 +224,16 @@ int nar_host_state_update_batch(int64_t* buffer, int64_t cap, const int64_t* ite
                                 int64_t* batch_scratch, int64_t* scratch, int64_t* recent_pop, double* pop_norm,
                                 int64_t* articles_pop, int64_t num_items, double min_norm_pop);
 
+/* ---- device-resident ClickedItemsState (same update as above, in HBM; STAGED: not yet on the default training loop).
+ *      old_items / old_ts [cap] -> new_items / new_ts [cap] (distinct buffers: ping-pong); all_items [Bg,T+1] =
+ *      [item_clicked | label_last_item], event_ts [Bg,T]; recent_pop [V] int64 scratch / output; pop_norm [V] float32
+ *      (what the graph reads), pop_norm64 [V] float64 or NULL; articles_pop [V] in/out; err[0] = 1 on an id outside
+ *      [0, V).  A batch without clicks leaves new_* untouched: the caller keeps using old_*.                        */
+int nar_state_update(const int64_t* old_items, const int64_t* old_ts, int64_t cap, const int64_t* all_items,
+                     const int64_t* event_ts, int64_t Bg, int64_t T, int64_t hours_ms, int64_t* new_items,
+                     int64_t* new_ts, int64_t* recent_pop, float* pop_norm, double* pop_norm64, int64_t* articles_pop,
+                     int64_t num_items, double min_norm_pop, int* err, void* stream);
+
 /* ---- small helpers ------------------------------------------------------------------ */
 /* out[c] += sum_r x[r,c]   (bias gradients)                                                */
 int nar_colsum_add(const float* x, int64_t rows, int64_t cols, int64_t ld, float* out, void* stream);

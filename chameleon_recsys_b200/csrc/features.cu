@@ -163,7 +163,7 @@ __device__ __forceinline__ float narrow_raw(int z, int a, int cm1, int ld, const
 }
 
 template <int WU>                                  // 128-bit vectors of wide table data per lane and row
-__global__ void __launch_bounds__(GATHER_WARPS * 32, 5)
+__global__ void __launch_bounds__(GATHER_WARPS * 32, (WU <= 4 ? 5 : 3))
 gather_features_kernel(const __grid_constant__ GatherArgs A, const GatherDesc* __restrict__ D,
                        const int32_t* __restrict__ row_pos, const int64_t* __restrict__ row_item,
                        int n_rows, int n_input, int n_cand,
@@ -580,7 +580,7 @@ extern "C" int nar_gather_features(nar_ctx* ctx, const nar_feature_plan* plan, c
   }
   for (int q = 0; q < plan->n_narrow; ++q) n_narrow_cols += plan->narrow_end[q] - plan->narrow_begin[q];
   if (n_ci > 12 || n_cf > 8 || n_me > 8 || n_wide > 2 || plan->row_ld > NAR_MAX_COLS || plan->row_ld > 0xffff ||
-      n_narrow_cols > nar::feat::GATHER_MAX_NARROW || n_tail > nar::feat::GATHER_MAX_TAIL || n_vec > 4 * 32 ||
+      n_narrow_cols > nar::feat::GATHER_MAX_NARROW || n_tail > nar::feat::GATHER_MAX_TAIL || n_vec > 8 * 32 ||
       n_rows > 0x7fffffffLL / 2 || (e_hi - e_lo) > 0x7fffffffLL ||     // table offsets are 32-bit (one flat parameter buffer)
       (reinterpret_cast<uintptr_t>(plan->gamma) & 15) || (reinterpret_cast<uintptr_t>(plan->beta) & 15) ||
       (reinterpret_cast<uintptr_t>(out) & 15)) return NAR_ERR_UNSUPPORTED;
@@ -630,7 +630,8 @@ extern "C" int nar_gather_features(nar_ctx* ctx, const nar_feature_plan* plan, c
 #define NAR_GATHER_LAUNCH(WU)                                                                                     \
   nar::feat::gather_features_kernel<WU><<<grid, nar::feat::GATHER_WARPS * 32, 0, as_stream(stream)>>>(            \
       A, D, row_pos, row_item, (int)n_rows, (int)n_input, (int)n_cand, event_timestamp, max_ts, out)
-  if (wu <= 1) NAR_GATHER_LAUNCH(1); else if (wu == 2) NAR_GATHER_LAUNCH(2); else if (wu == 3) NAR_GATHER_LAUNCH(3); else NAR_GATHER_LAUNCH(4);
+  if (wu <= 1) NAR_GATHER_LAUNCH(1); else if (wu == 2) NAR_GATHER_LAUNCH(2); else if (wu == 3) NAR_GATHER_LAUNCH(3);
+  else if (wu == 4) NAR_GATHER_LAUNCH(4); else if (wu <= 6) NAR_GATHER_LAUNCH(6); else NAR_GATHER_LAUNCH(8);   // up to 1024 wide floats per row
 #undef NAR_GATHER_LAUNCH
   NAR_LAUNCH_CHECK();
   return NAR_OK;

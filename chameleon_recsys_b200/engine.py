@@ -157,7 +157,12 @@ class NarEngine:
         need = max(1, rows) * cols
         t = self._bufs.get(name)
         if t is None or t.numel() < need or t.dtype != dtype:
-            cap = max(int(need * 1.25) + 1024, max(1, cap_rows) * cols)
+            cap = int(need * 1.25) + 1024
+            worst = max(1, cap_rows) * cols
+            # worst-case sizing only while it is cheap: the stress configuration (8192 sessions x 500 negatives) would
+            # ask for a terabyte; beyond 8 GiB per buffer the 1.25x growth policy applies instead
+            if worst * torch.empty((), dtype=dtype).element_size() <= (8 << 30):
+                cap = max(cap, worst)
             t = torch.empty(cap, device=self.dev, dtype=dtype)
             self._bufs[name] = t
         return t[:max(1, rows) * cols].view(max(1, rows), cols)

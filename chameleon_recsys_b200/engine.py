@@ -99,6 +99,7 @@ class NarEngine:
         self._side = None
         self._prep_flip = 0
         self.use_side_stream = os.environ.get('NAR_SIDE_STREAM', '1') == '1'
+        self._slot_events: Dict[str, torch.cuda.Event] = {}       # prepare() slot -> end of the last step that read it
         self._aux = None
         self.use_aux_stream = os.environ.get('NAR_AUX_STREAM', '1') == '1'
         self.split_fwd = os.environ.get('NAR_SPLIT_FWD', '1') == '1'     # session branch under the candidate CAR GEMMs
@@ -367,6 +368,11 @@ class NarEngine:
         slot = ('/ahead%d' % self._prep_flip) if stream is not None else ''
         cur = torch.cuda.current_stream()
         run_on = stream if stream is not None else cur
+        # two result slots alternate: the step that consumed this slot two prepare() calls ago may still be running (its
+        # gather backward reads the row lists at the very end), so the side stream waits for that step's end first
+        last_use = self._slot_events.get(slot) if stream is not None else None
+        if last_use is not None:
+            run_on.wait_event(last_use)
         with torch.cuda.stream(run_on):
             need = ops.sample_negatives_workspace(Bg, T + 1, self.buf_len, K)
             if self._sampler_ws is None or self._sampler_ws.numel() < need:
@@ -389,13 +395,19 @@ class NarEngine:
                 ev = torch.cuda.Event()
                 ev.record(run_on)
         st['prep'] = {'neg': neg, 'neg_local': neg_local, 'row_pos': row_pos, 'row_item': row_item, 'stats': stats,
-                      'event': ev, 'step_id': step_id}
+                      'event': ev, 'step_id': step_id, 'slot': slot}
         return st
 
     def step(self, st: dict, train: bool = True, keep: bool = False) -> dict:
         """Run one step on staged inputs.  Returns device tensors (loss parts, logits, negatives)."""
         with ops.on_stream(torch.cuda.current_stream()):      # one stream lookup per step instead of one per launch
-            return self._step(st, train, keep)
+            out = self._step(st, train, keep)
+        prep = st.get('prep')
+        if prep is not None and prep.get('slot'):             # ran-ahead results: mark when this step is done with them
+            ev = torch.cuda.Event()
+            ev.record()
+            self._slot_events[prep['slot']] = ev
+        return out
 
     def _step(self, st: dict, train: bool, keep: bool) -> dict:
         t = st['t']

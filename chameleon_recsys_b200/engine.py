@@ -100,6 +100,7 @@ class NarEngine:
         self._prep_flip = 0
         self.use_side_stream = os.environ.get('NAR_SIDE_STREAM', '1') == '1'
         self._slot_events: Dict[str, torch.cuda.Event] = {}       # prepare() slot -> end of the last step that read it
+        self._pin_events: Dict[str, torch.cuda.Event] = {}        # staging slot -> its last H2D copy
         self._aux = None
         self.use_aux_stream = os.environ.get('NAR_AUX_STREAM', '1') == '1'
         self.split_fwd = os.environ.get('NAR_SPLIT_FWD', '1') == '1'     # session branch under the candidate CAR GEMMs
@@ -208,13 +209,20 @@ class NarEngine:
         total = round_up(off, 16)
         worst = total + 4 * (per * T - pos_idx.size) + 64       # pos_idx is the only part whose size varies step to step
         pin = self._pin(slot, worst)
+        busy = self._pin_events.get(slot)
+        if busy is not None:
+            busy.synchronize()                # the previous H2D copy out of this pinned slot (issued >= 2 steps ago) is done
         pin_np = pin.numpy()
         for name, arr, dt in parts:
             o, nel, _, _ = offs[name]
             pin_np[o:o + nel * np.dtype(dt).itemsize].view(dt)[:] = arr.reshape(-1)
         dev = self._buf(slot, total, 1, torch.uint8, cap_rows=worst).view(-1)
-        with torch.cuda.stream(stream if stream is not None else torch.cuda.current_stream()):
+        copy_stream = stream if stream is not None else torch.cuda.current_stream()
+        with torch.cuda.stream(copy_stream):
             dev[:total].copy_(pin[:total], non_blocking=True)
+        copied = torch.cuda.Event()
+        copied.record(copy_stream)
+        self._pin_events[slot] = copied
         tmap = {np.int64: torch.int64, np.float32: torch.float32, np.int32: torch.int32}
         tens = {}
         for name, (o, nel, dt, shp) in offs.items():

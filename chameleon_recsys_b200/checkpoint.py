@@ -49,7 +49,7 @@ def save(path: str, engine, clicked_items_state=None) -> str:
             arrays['state/' + f] = np.asarray(getattr(clicked_items_state, f))
         arrays['state/current_step'] = np.asarray(clicked_items_state.current_step, dtype=np.int64)
     os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
-    tmp = path + '.tmp.npz'
+    tmp = '%s.tmp%d.npz' % (path, os.getpid())      # unique per process: writers never share a temp file
     np.savez(tmp, **arrays)
     os.replace(tmp, path)                     # atomic: a reader never sees a half-written checkpoint
     return path

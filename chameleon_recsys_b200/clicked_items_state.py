@@ -1,18 +1,13 @@
-"""Host state of the recent-clicks buffer and recent popularity (numpy).
+"""Host state of the recent-clicks buffer and recent popularity.
 
-Mirror of the hot-path part of the reference class of the same name
-(nar_module/nar/clicked_items_state.py:10-250): same constructor, same method
-names, same arrays.  Out of scope: the co-occurrence
-CSR matrix (:252-255, benchmarks only), cold-start bookkeeping (:97-123, :196-203).
-
-Buffer semantics (clicked_items_state.py:206-228):
-  * ``[max_size, 2]`` int64 rows (article_id, click_timestamp_ms), newest first;
-  * on update the batch is reversed and prepended, rows older than
-    ``min(batch ts) - hours`` are dropped first (that also drops zero padding rows),
-    then the buffer is clipped / zero padded back to ``max_size``.
-Popularity (clicked_items_state.py:231-246):
-  * ``articles_recent_pop`` = bincount of nonzero buffer ids,
-  * ``articles_recent_pop_norm`` = max(pop / (sum(pop)+1), 1/recent_clicks_for_normalization) (float64).
+Mirror of the hot-path part of the reference class of the same name (nar_module/nar/clicked_items_state.py:10-250):
+same constructor, same method names, same arrays.  The update itself (``update_items_state`` :187-250, and the
+hook's batch flattening nar_model.py:1635-1646) is ONE C pass in libnar_b200 (``nar_host_state_update[_batch]``,
+csrc/host_state.cu, host code, ~40 us per G1 step); there is no numpy fallback - without the library every update
+raises.  The numpy specification it is bit-checked against lives with the test infrastructure
+(oracle/clicked_items_state_ref.py, pinned to fixtures produced by the reference class itself).
+Out of scope: the co-occurrence CSR matrix (:252-255, benchmarks only), cold-start
+bookkeeping (:97-123, :196-203).
 """
 from __future__ import annotations
 
@@ -32,7 +27,8 @@ class ClickedItemsState:
     def reset_state(self):
         self.articles_pop = np.zeros(shape=[self.num_items], dtype=np.int64)
         self.articles_recent_pop = np.zeros(shape=[self.num_items], dtype=np.int64)
-        self._update_recent_pop_norm(self.articles_recent_pop)
+        # empty buffer: pop / (0 + 1) floored at 1 / recent_clicks_for_normalization (clicked_items_state.py:240-246)
+        self.articles_recent_pop_norm = np.full(self.num_items, 1.0 / self.recent_clicks_for_normalization, dtype=np.float64)
         self.pop_recent_clicks_buffer = np.zeros(shape=[self.recent_clicks_buffer_max_size, 2], dtype=np.int64)
         self.pop_recent_buffer_article_id_column = 0
         self.pop_recent_buffer_timestamp_column = 1
@@ -75,79 +71,55 @@ class ClickedItemsState:
     def get_max_timestamp_recent_clicks(self):
         return np.max(self.pop_recent_clicks_buffer[:, self.pop_recent_buffer_timestamp_column])
 
-    # -- update (clicked_items_state.py:187-250)
+    # -- update (clicked_items_state.py:187-250): the C pass
+    @staticmethod
+    def _lib():
+        from . import _lib as nl
+        return nl.load()                      # raises NarError when the library is not built
+
     def update_items_state(self, batch_clicked_items, batch_clicked_timestamps):
-        """One call per step.  Runs the single-pass C implementation in libnar_b200 (``nar_host_state_update``, host
-        code) when the library is built - the numpy restatement below is the specification it is tested against
-        (tests/test_host_state.py) and costs ~0.8 ms per G1 step, which made the end-to-end loop host bound."""
-        if self._native_update(batch_clicked_items, batch_clicked_timestamps):
-            return
-        self.update_items_state_numpy(batch_clicked_items, batch_clicked_timestamps)
-
-    def update_items_state_numpy(self, batch_clicked_items, batch_clicked_timestamps):
-        self._update_recently_clicked_items_buffer(batch_clicked_items, batch_clicked_timestamps)
-        self._update_recent_pop_items()
-        self._update_pop_items(batch_clicked_items)
-
-    _lib = None           # class-level cache: ctypes handle, or False when the library is not available
-
-    @classmethod
-    def _native(cls):
-        if cls._lib is None:
-            try:
-                from . import _lib as nl
-                cls._lib = nl.load()
-            except Exception:  # noqa: BLE001  (library not built: the numpy path is complete)
-                cls._lib = False
-        return cls._lib
-
-    def update_from_batch(self, clicked_items, clicked_timestamps, last_item_label):
-        """ItemsStateUpdaterHook.after_run in one call: ``batch_clicks_for_state_update`` + ``update_items_state``
-        (both stay as the numpy specification; the C path does the same in one pass over the padded batch)."""
-        lib = self._native()
-        ci = np.ascontiguousarray(clicked_items, dtype=np.int64)
-        if lib is False or ci.ndim != 2:
-            items, ts = batch_clicks_for_state_update(clicked_items, clicked_timestamps, last_item_label)
-            if items.size:
-                self.update_items_state(items, ts)
-            return
-        ct = np.ascontiguousarray(clicked_timestamps, dtype=np.int64)
-        ll = np.ascontiguousarray(last_item_label, dtype=np.int64).reshape(-1)
-        B, T = ci.shape
-        bs = getattr(self, '_batch_scratch', None)
-        if bs is None or bs.size < 2 * B * (T + 1):
-            bs = self._batch_scratch = np.empty(2 * B * (T + 1), dtype=np.int64)
-        ok = self._native_call(lambda buf, scratch, recent, norm, pop, hours_ms: lib.nar_host_state_update_batch(
-            buf.ctypes.data, buf.shape[0], ci.ctypes.data, ct.ctypes.data, ll.ctypes.data, B, T, hours_ms, bs.ctypes.data,
-            scratch.ctypes.data, recent.ctypes.data, norm.ctypes.data, pop.ctypes.data, self.num_items,
-            1.0 / self.recent_clicks_for_normalization), keep_pop_on_empty=not (ci.any() or ll.any()))
-        if not ok:                            # unusual array layout: the numpy specification handles everything
-            items, ts = batch_clicks_for_state_update(clicked_items, clicked_timestamps, last_item_label)
-            if items.size:
-                self.update_items_state_numpy(items, ts)
-
-    def _native_update(self, batch_clicked_items, batch_clicked_timestamps) -> bool:
-        lib = self._native()
-        if lib is False:
-            return False
+        """One call per step with the batch's non-padded clicks in batch order (what the hook hands over)."""
+        lib = self._lib()
         items = np.ascontiguousarray(batch_clicked_items, dtype=np.int64).reshape(-1)
         ts = np.ascontiguousarray(batch_clicked_timestamps, dtype=np.int64).reshape(-1)
-        if items.size == 0 or items.size != ts.size:
-            return False
-        return self._native_call(lambda buf, scratch, recent, norm, pop, hours_ms: lib.nar_host_state_update(
+        if items.size != ts.size:
+            raise ValueError('items / timestamps differ in length')
+        if items.size == 0:
+            raise ValueError('update_items_state needs at least one click (np.min of an empty batch in the reference)')
+        self._call(lambda buf, scratch, recent, norm, pop, hours_ms: lib.nar_host_state_update(
             buf.ctypes.data, buf.shape[0], items.ctypes.data, ts.ctypes.data, items.size, hours_ms, scratch.ctypes.data,
             recent.ctypes.data, norm.ctypes.data, pop.ctypes.data, self.num_items,
             1.0 / self.recent_clicks_for_normalization))
 
-    def _native_call(self, fn, keep_pop_on_empty: bool = False) -> bool:
-        if keep_pop_on_empty:
-            return True                       # nothing but padding in the batch: the hook does not touch the state
+    def update_from_batch(self, clicked_items, clicked_timestamps, last_item_label):
+        """ItemsStateUpdaterHook.after_run in one call (nar_model.py:1635-1650): the padded [B,T] batch + [B,1] last
+        labels are flattened, padding dropped and folded in, in one pass.  A batch of nothing but padding leaves the
+        state alone like the hook does."""
+        lib = self._lib()
+        ci = np.ascontiguousarray(clicked_items, dtype=np.int64)
+        if ci.ndim != 2:
+            raise ValueError('clicked_items must be [B, T]')
+        ct = np.ascontiguousarray(clicked_timestamps, dtype=np.int64)
+        ll = np.ascontiguousarray(last_item_label, dtype=np.int64).reshape(-1)
+        B, T = ci.shape
+        if ct.shape != (B, T) or ll.shape != (B,):
+            raise ValueError('clicked_timestamps must be [B, T] and last_item_label [B, 1]')
+        if not (ci.any() or ll.any()):
+            return
+        bs = getattr(self, '_batch_scratch', None)
+        if bs is None or bs.size < 2 * B * (T + 1):
+            bs = self._batch_scratch = np.empty(2 * B * (T + 1), dtype=np.int64)
+        self._call(lambda buf, scratch, recent, norm, pop, hours_ms: lib.nar_host_state_update_batch(
+            buf.ctypes.data, buf.shape[0], ci.ctypes.data, ct.ctypes.data, ll.ctypes.data, B, T, hours_ms, bs.ctypes.data,
+            scratch.ctypes.data, recent.ctypes.data, norm.ctypes.data, pop.ctypes.data, self.num_items,
+            1.0 / self.recent_clicks_for_normalization))
+
+    def _call(self, fn):
         buf = self.pop_recent_clicks_buffer
-        if buf.dtype != np.int64 or not buf.flags['C_CONTIGUOUS'] or not buf.flags['WRITEABLE'] or \
-                buf.shape != (self.recent_clicks_buffer_max_size, 2):
+        if buf.dtype != np.int64 or not buf.flags['C_CONTIGUOUS'] or not buf.flags['WRITEABLE']:
             buf = np.ascontiguousarray(buf, dtype=np.int64).copy()
-            if buf.shape != (self.recent_clicks_buffer_max_size, 2):
-                return False
+        if buf.shape != (self.recent_clicks_buffer_max_size, 2):
+            raise ValueError('pop_recent_clicks_buffer must be [recent_clicks_buffer_max_size, 2]')
         scratch = getattr(self, '_scratch', None)
         if scratch is None or scratch.shape != buf.shape:
             scratch = self._scratch = np.empty_like(buf)
@@ -170,52 +142,13 @@ class ClickedItemsState:
         self.articles_recent_pop = recent
         self.articles_recent_pop_norm = norm
         self.articles_pop = pop
-        return True
-
-    def _update_recently_clicked_items_buffer(self, batch_clicked_items, batch_clicked_timestamps):
-        batch = np.hstack([np.asarray(batch_clicked_items, dtype=np.int64).reshape(-1, 1),
-                           np.asarray(batch_clicked_timestamps, dtype=np.int64).reshape(-1, 1)])
-        batch = batch[::-1]                      # newest click first
-        min_timestamp_batch = np.min(batch_clicked_timestamps)
-        self.truncate_last_hours_recent_clicks_buffer(min_timestamp_batch)
-        buf = np.vstack([batch, self.pop_recent_clicks_buffer])[:self.recent_clicks_buffer_max_size]
-        if buf.shape[0] < self.recent_clicks_buffer_max_size:
-            buf = np.vstack([buf, np.zeros(shape=[self.recent_clicks_buffer_max_size - buf.shape[0], 2],
-                                           dtype=np.int64)])
-        self.pop_recent_clicks_buffer = buf
-
-    def truncate_last_hours_recent_clicks_buffer(self, reference_timestamp):
-        MILISECS_BY_HOUR = 1000 * 60 * 60
-        thr = reference_timestamp - int(self.recent_clicks_buffer_hours * MILISECS_BY_HOUR)
-        ts = self.pop_recent_clicks_buffer[:, self.pop_recent_buffer_timestamp_column]
-        self.pop_recent_clicks_buffer = self.pop_recent_clicks_buffer[ts >= thr]
-
-    def _update_recent_pop_items(self):
-        items = self.pop_recent_clicks_buffer[:, self.pop_recent_buffer_article_id_column]
-        nz = items[np.nonzero(items)]
-        self.articles_recent_pop = np.bincount(nz, minlength=self.num_items).astype(np.int64)
-        self._update_recent_pop_norm(self.articles_recent_pop)
-
-    def _update_recent_pop_norm(self, articles_recent_pop):
-        min_norm_pop = 1.0 / self.recent_clicks_for_normalization
-        self.articles_recent_pop_norm = np.maximum(articles_recent_pop / (articles_recent_pop.sum() + 1),
-                                                   [min_norm_pop])
-
-    def _update_pop_items(self, batch_items_nonzero):
-        self.articles_pop += np.bincount(np.asarray(batch_items_nonzero, dtype=np.int64),
-                                         minlength=self.num_items).astype(np.int64)
 
 
 def batch_clicks_for_state_update(clicked_items, clicked_timestamps, last_item_label):
-    """ItemsStateUpdaterHook.after_run, train-mode part (nar_model.py:1635-1646).
-
-    clicked_items [B,T] i64, clicked_timestamps [B,T] i64, last_item_label [B,1] i64
-    -> (items_nonzero, timestamps_nonzero) row-major flattened, padding dropped; the
-    last label inherits the session's max timestamp.
-    """
-    batch_clicked_items = np.concatenate([clicked_items, last_item_label], axis=1)
-    flat = batch_clicked_items.reshape(-1)
-    nz = np.nonzero(flat)
-    last_ts = np.max(clicked_timestamps, axis=1).reshape(-1, 1)
-    ts = np.concatenate([clicked_timestamps, last_ts], axis=1).reshape(-1)
-    return flat[nz], ts[nz]
+    """ItemsStateUpdaterHook.after_run, train-mode part (nar_model.py:1635-1646): the hook's flattening, for callers
+    that hand ``update_items_state`` the reference's way ([B,T] ids / timestamps + [B,1] last label ->
+    (items_nonzero, timestamps_nonzero), the last label carrying its session's maximum timestamp)."""
+    allc = np.concatenate([clicked_items, last_item_label], axis=1).reshape(-1)
+    ts = np.concatenate([clicked_timestamps, np.max(clicked_timestamps, axis=1).reshape(-1, 1)], axis=1).reshape(-1)
+    keep = np.nonzero(allc)
+    return allc[keep], ts[keep]

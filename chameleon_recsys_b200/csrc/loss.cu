@@ -168,7 +168,7 @@ constexpr int RANK_WARPS = 4;
 
 __global__ void __launch_bounds__(RANK_WARPS * 32)
 rank_candidates_kernel(const float* __restrict__ logits, const int64_t* __restrict__ cand_ids, int64_t n_pos, int n_cand,
-                       int top_n, int64_t* __restrict__ pred_ids, float* __restrict__ pred_probs, float* __restrict__ metrics) {
+                       int top_n, int64_t* __restrict__ pred_ids, float* __restrict__ pred_probs, double* __restrict__ metrics) {
   extern __shared__ float sh[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t l = (int64_t)blockIdx.x * RANK_WARPS + w;
@@ -191,8 +191,10 @@ rank_candidates_kernel(const float* __restrict__ logits, const int64_t* __restri
     if (pred_ids) pred_ids[l * n_cand + rank] = cand_ids[l * n_cand + i];
     if (pred_probs) pred_probs[l * n_cand + rank] = pi;
     if (i == 0 && metrics) {
-      if (rank < top_n) { atomicAdd(metrics + 0, 1.0f); atomicAdd(metrics + 1, 1.0f / (float)(rank + 1)); }
-      atomicAdd(metrics + 2, 1.0f);
+      // float64 accumulators: hit / label counts stay exact (integers below 2^53), the reciprocal-rank sum keeps
+      // ~1e-16 relative rounding whatever the order of the atomics
+      if (rank < top_n) { atomicAdd(metrics + 0, 1.0); atomicAdd(metrics + 1, 1.0 / (double)(rank + 1)); }
+      atomicAdd(metrics + 2, 1.0);
     }
   }
 }
@@ -250,7 +252,7 @@ extern "C" int nar_cosine_softmax_ce(const float* cand, const float* pred, int64
 }
 
 extern "C" int nar_rank_candidates(const float* logits, const int64_t* cand_ids, int64_t n_pos, int64_t n_cand, int32_t top_n,
-                                   int64_t* pred_ids, float* pred_probs, float* metrics, void* stream) {
+                                   int64_t* pred_ids, float* pred_probs, double* metrics, void* stream) {
   if (!logits || !cand_ids) return NAR_ERR_INVALID;
   if (n_pos <= 0) return NAR_OK;
   if (n_cand <= 0 || top_n < 0) return NAR_ERR_INVALID;

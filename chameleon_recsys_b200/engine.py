@@ -645,7 +645,7 @@ class NarEngine:
                   step_id: Optional[int] = None, keep: bool = False) -> dict:
         """One evaluation batch: negatives with this engine's (eval) sampling hparams, forward, loss, then
         rank_items_by_predicted_prob (nar_model.py:777-795) and the streaming HR@n / MRR@n sums (:835-885).
-        ``metrics`` [3] float32 device accumulator {hits, sum of reciprocal ranks, valid labels}."""
+        ``metrics`` [3] float64 device accumulator {hits, sum of reciprocal ranks, valid labels} (counts stay exact)."""
         st = self.stage(features, labels, buffer, pop_norm, slot='eval')
         if step_id is not None:
             self.prepare(st, step_id)
@@ -653,7 +653,8 @@ class NarEngine:
         out = self.step(st, train=False, keep=keep)
         L, n_cand = st['L'], self.K + 1
         if metrics is None:
-            metrics = torch.zeros(3, device=self.dev)
+            metrics = torch.zeros(3, device=self.dev, dtype=torch.float64)
+        assert metrics.dtype == torch.float64
         out['metrics'] = metrics
         if L > 0:
             prep = st['prep']

@@ -203,7 +203,15 @@ class Estimator:
         for h in spec.training_chief_hooks:
             h.end()
         if self.model_dir:
-            self.save_checkpoint()                                   # CheckpointSaverHook at the end of train()
+            # CheckpointSaverHook at the end of train().  Data parallel: weights, Adam slots and the host state are
+            # identical on every rank, so rank 0 alone writes and the others wait for the file to be complete.
+            if eng.world > 1:
+                import torch
+                if eng.rank == 0:
+                    self.save_checkpoint()
+                torch.distributed.barrier(group=eng.pg)
+            else:
+                self.save_checkpoint()
         return self
 
     def evaluate(self, input_fn, steps: Optional[int] = None, hooks=None, name=None) -> dict:
@@ -229,9 +237,19 @@ class Estimator:
         spec = self._eval_spec
         if self._spec is not None:
             spec.model.engine.share_params(self._spec.model.engine)        # "restore the latest checkpoint"
+        else:
+            # fresh Estimator over an existing model_dir: tf.estimator.Estimator.evaluate restores the latest checkpoint
+            # (nar_trainer_gcom.py:523) and fails when there is none - never evaluate randomly initialised weights
+            latest = ckpt.latest_checkpoint(self.model_dir)
+            if latest is None:
+                raise ValueError('Estimator.evaluate: no trained model - call train() first or point model_dir at a '
+                                 'directory holding a checkpoint (model_dir=%r)' % (self.model_dir,))
+            if getattr(self, '_eval_restored', None) != latest:
+                ckpt.restore(latest, spec.model.engine, None)               # weights + step; the hook snapshots the state
+                self._eval_restored = latest
         for h in spec.evaluation_hooks:
             h.begin()
-        metrics = torch.zeros(3, device=spec.model.engine.dev)
+        metrics = torch.zeros(3, device=spec.model.engine.dev, dtype=torch.float64)
         update = spec.eval_metric_ops['hitrate_at_n']
         n, loss_sum = 0, 0.0
         while nxt is not None:

@@ -11,7 +11,7 @@ from typing import Dict
 
 import numpy as np
 
-from .clicked_items_state import ClickedItemsState, batch_clicks_for_state_update
+from .clicked_items_state import ClickedItemsState
 from .datasets import prepare_dataset_iterator
 from .hparams import (NARHParams, Workload, get_articles_features_config,
                       get_internal_enabled_features_config, get_session_features_config, workload)
@@ -43,7 +43,7 @@ class Problem:
                                         truncate_session_length=self.hp.truncate_session_length)
 
 
-def make_problem(name_or_wl, profile=None, session_len=None, seed: int = 42, **hp_overrides) -> Problem:
+def make_problem(name_or_wl, profile=None, session_len=None, seed: int = 42, state_cls=None, **hp_overrides) -> Problem:
     wl = name_or_wl if isinstance(name_or_wl, Workload) else workload(name_or_wl, profile, session_len)
     if hp_overrides:
         wl.hp = wl.hp.copy(**hp_overrides)
@@ -55,7 +55,7 @@ def make_problem(name_or_wl, profile=None, session_len=None, seed: int = 42, **h
     acr, meta = make_catalog(V, E, acfg, hp.content_embedding_scale_factor, seed=seed)
     plan = FeaturePlan(scfg, acfg, icfg, hp.max_cardinality_for_ohe, E, V)
     layout = ParamLayout(plan, hp.CAR_embedding_size, hp.rnn_units, hp.rnn_num_layers)
-    state = ClickedItemsState(hp.recent_clicks_buffer_hours, hp.recent_clicks_buffer_max_size,
+    state = (state_cls or ClickedItemsState)(hp.recent_clicks_buffer_hours, hp.recent_clicks_buffer_max_size,
                               hp.recent_clicks_for_normalization, V)
     stream = SessionStream(V, scfg, hp.truncate_session_length, wl.session_len, seed=seed,
                            sessions_per_tick=hp.batch_size)
@@ -67,6 +67,5 @@ def warm_state(problem: Problem, n_batches: int):
     it = problem.input_fn()
     for _ in range(n_batches):
         feats, labels = it.get_next()
-        items, ts = batch_clicks_for_state_update(feats['item_clicked'], feats['event_timestamp'],
-                                                  labels['label_last_item'])
-        problem.clicked_items_state.update_items_state(items, ts)
+        problem.clicked_items_state.update_from_batch(feats['item_clicked'], feats['event_timestamp'],
+                                                      labels['label_last_item'])

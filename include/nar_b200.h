@@ -207,7 +207,7 @@ int nar_cosine_softmax_ce(const float* cand, const float* pred, int64_t n_pos, i
  *      softmax probability, descending, ties to the lower candidate index (top_k order).  metrics[0] += number of
  *      positions whose positive is in the top_n, metrics[1] += sum of 1/rank for those, metrics[2] += n_pos.       */
 int nar_rank_candidates(const float* logits, const int64_t* cand_ids, int64_t n_pos, int64_t n_cand, int32_t top_n,
-                        int64_t* pred_ids, float* pred_probs, float* metrics, void* stream);
+                        int64_t* pred_ids, float* pred_probs, double* metrics /*[3] float64*/, void* stream);
 
 /* ---- host state (CPU, no CUDA): ClickedItemsState.update_items_state (clicked_items_state.py:187-250) in one pass.
  *      buffer [cap,2] int64 {item, timestamp} newest first, zero padded (in/out); batch_items / batch_ts: the step's

@@ -1,11 +1,9 @@
-"""Device-resident ClickedItemsState (staged) against the host class, batch by batch.
-Not part of the `-m gpu` gate yet: it runs wherever CUDA is available (`pytest tests/test_device_state.py` on a GPU
-box) and is skipped elsewhere; it moves under the gpu marker together with the engine wiring."""
+"""Device-resident ClickedItemsState against the host class, batch by batch."""
 import numpy as np
 import pytest
 
 torch = pytest.importorskip('torch')
-pytestmark = pytest.mark.skipif(not torch.cuda.is_available(), reason='needs a CUDA device')
+pytestmark = pytest.mark.gpu
 
 
 def test_device_state_tracks_host_state():

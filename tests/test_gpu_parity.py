@@ -83,8 +83,56 @@ def test_full_step_parity_g1_shapes():
     _check_steps(res)
 
 
+def test_full_step_parity_g1_full_batch():
+    """BASELINE configs[1] at its REAL size (batch 256, seq <= 20, K 50, 46K items): one full step vs the fp32 oracle
+    (the oracle needs ~3 s for it)."""
+    import torch
+    from tools import gpu_step_check as g
+    res = g.run_case('g1', 'B', 30, 1, oracle_dtype=torch.float32)
+    assert res['steps'][0]['B'] == 256
+    _check_steps(res)
+
+
+@pytest.mark.parametrize('bwd', [1, 3])
+def test_unsynced_trajectory_g1(bwd):
+    """30 steps WITHOUT reloading the oracle's state into the engine: each side follows its own Adam trajectory.  The
+    loss must stay within 1e-3 relative at every step - the test that says whether single-pass TF32 backward GEMMs
+    (bwd=1; the reference's gradients are fp32) are acceptable; bwd=3 (3xTF32 backward) is the control."""
+    import json
+    import torch
+    from tools import gpu_step_check as g
+    res = g.run_trajectory('g1', 'B', 30, 30, hp_over=dict(batch_size=64), oracle_dtype=torch.float32,
+                           engine_kw=dict(bwd_precision=bwd))
+    os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+    with open(os.path.join(ROOT, 'gpurun_out', 'trajectory_bwd%d.json' % bwd), 'w') as f:
+        json.dump(res, f, indent=1)
+    assert all(s['neg_equal'] for s in res['steps'])
+    assert res['max_rel'] < 1e-3, [(s['step'], s['rel']) for s in res['steps'] if s['rel'] >= 1e-3]
+
+
+def test_nccl_two_ranks_match_single():
+    """Real NCCL: a 2-rank data-parallel run (torchrun, one rank per GPU) reproduces the 1-rank run of the same global
+    batch - negatives bit-exact, loss within 1e-5, all-reduced gradient within 1e-4 of its max, weights within Adam's
+    +-lr noise on near-zero gradients.  Needs 2 GPUs (skipped on a 1-GPU box; run with `gpurun --gpus 2`)."""
+    import json
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+           '--master-port', '29617', os.path.join(ROOT, 'tools', 'nccl_equiv.py')]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    line = [x for x in r.stdout.splitlines() if x.startswith('NCCL_EQUIV ')][-1]
+    res = json.loads(line[len('NCCL_EQUIV '):])
+    assert res['negatives_equal']
+    assert res['loss_rel_max'] < 1e-5 and res['reg_rel_max'] < 1e-5, res
+    assert res['grad_rel_max_last_step'] < 1e-4, res
+    assert res['param_diff_median'] < 1e-6 and res['param_diff_max'] <= 2.5 * res['steps'] * res['lr'], res
+
+
 def test_full_size_properties_g1():
-    """BASELINE config[1] at full size: size-independent properties (the oracle is too slow to run every step)."""
+    """BASELINE config[1] at full size over several steps: size-independent properties of every step."""
     import torch
     from chameleon_recsys_b200.harness import make_problem, warm_state
     from tools.gpu_step_check import make_engine
@@ -169,7 +217,7 @@ def test_eval_ranking_and_metrics_vs_oracle():
     eng.set_params(logical); orc.set_params(logical)
     it = pb.input_fn()
     top_n = 3
-    metrics = torch.zeros(3, device='cuda')
+    metrics = torch.zeros(3, device='cuda', dtype=torch.float64)
     tot = np.zeros(3)
     for step in range(3):
         f, l = it.get_next()

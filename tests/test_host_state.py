@@ -1,5 +1,7 @@
 """ClickedItemsState / datasets / plan (host logic) against fixtures generated from the reference's own
-classes (tests/golden/make_state_golden.py) and against the reference's documented semantics."""
+classes (tests/golden/make_state_golden.py) and against the reference's documented semantics.  Both the product
+class (one C pass in libnar_b200) and the numpy specification (oracle/clicked_items_state_ref.py) are pinned to the
+reference's outputs."""
 import os
 
 import numpy as np
@@ -13,11 +15,14 @@ from chameleon_recsys_b200.hparams import get_embedding_size, workload
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def test_state_matches_reference_golden():
+@pytest.mark.parametrize('which', ['product_c_pass', 'numpy_spec'])
+def test_state_matches_reference_golden(which):
+    from oracle.clicked_items_state_ref import ClickedItemsStateRef
+    cls = ClickedItemsState if which == 'product_c_pass' else ClickedItemsStateRef
     g = np.load(os.path.join(HERE, 'golden', 'state_golden.npz'))
     for ci in range(3):
         hours, max_size, n_norm, V = g['c%d_cfg' % ci]
-        st = ClickedItemsState(float(hours), int(max_size), int(n_norm), int(V))
+        st = cls(float(hours), int(max_size), int(n_norm), int(V))
         for step in range(6):
             st.update_items_state(g['c%d_items_%d' % (ci, step)], g['c%d_ts_%d' % (ci, step)])
             assert np.array_equal(st.pop_recent_clicks_buffer, g['c%d_buffer_%d' % (ci, step)])
@@ -162,10 +167,11 @@ def test_native_state_update_equals_numpy_spec():
     exercises the hour cut-off, the clip at max size, padding and repeated ids."""
     from chameleon_recsys_b200 import _lib
     from chameleon_recsys_b200.clicked_items_state import ClickedItemsState
+    from oracle.clicked_items_state_ref import ClickedItemsStateRef
     _lib.load()                                                   # the library must be there: build() made it
     rs = np.random.RandomState(1)
     a = ClickedItemsState(0.5, 300, 50, 400)
-    b = ClickedItemsState(0.5, 300, 50, 400)
+    b = ClickedItemsStateRef(0.5, 300, 50, 400)
     t = 1_500_000_000_000
     for step in range(60):
         n = int(rs.randint(1, 90))
@@ -173,8 +179,7 @@ def test_native_state_update_equals_numpy_spec():
         t += int(rs.randint(0, 600_000))                         # up to 10 min between batches, 30 min window
         ts = (t + rs.randint(-200_000, 200_000, n)).astype(np.int64)
         a.update_items_state(items, ts)                           # native
-        b.update_items_state_numpy(items, ts)                     # spec
-        assert ClickedItemsState._lib not in (None, False)
+        b.update_items_state(items, ts)                           # spec
         assert np.array_equal(a.get_recent_clicks_buffer(), b.get_recent_clicks_buffer()), step
         assert np.array_equal(a.pop_recent_clicks_buffer, b.pop_recent_clicks_buffer), step
         assert np.array_equal(a.get_articles_recent_pop(), b.get_articles_recent_pop())
@@ -188,15 +193,18 @@ def test_native_state_update_equals_numpy_spec():
 def test_native_update_from_batch_equals_hook_spec():
     """update_from_batch (one C pass over the padded batch) == batch_clicks_for_state_update + numpy update."""
     from chameleon_recsys_b200.clicked_items_state import ClickedItemsState
+    from oracle import clicked_items_state_ref as ref
     pb = make_problem('tiny', profile='B')
     it = pb.input_fn()
     a = ClickedItemsState(1.0, 400, 100, pb.plan.num_items)
-    b = ClickedItemsState(1.0, 400, 100, pb.plan.num_items)
+    b = ref.ClickedItemsStateRef(1.0, 400, 100, pb.plan.num_items)
     for step in range(12):
         f, l = it.get_next()
         a.update_from_batch(f['item_clicked'], f['event_timestamp'], l['label_last_item'])
-        items, ts = batch_clicks_for_state_update(f['item_clicked'], f['event_timestamp'], l['label_last_item'])
-        b.update_items_state_numpy(items, ts)
+        items, ts = ref.batch_clicks_for_state_update(f['item_clicked'], f['event_timestamp'], l['label_last_item'])
+        i2, t2 = batch_clicks_for_state_update(f['item_clicked'], f['event_timestamp'], l['label_last_item'])
+        assert np.array_equal(items, i2) and np.array_equal(ts, t2)
+        b.update_items_state(items, ts)
         assert np.array_equal(a.pop_recent_clicks_buffer, b.pop_recent_clicks_buffer), step
         assert np.array_equal(a.get_articles_recent_pop_norm(), b.get_articles_recent_pop_norm())
         assert np.array_equal(a.get_articles_pop(), b.get_articles_pop())

@@ -145,6 +145,39 @@ def run_case(name, profile, warm, n_steps, hp_over=None, oracle_dtype=torch.floa
     return res
 
 
+def run_trajectory(name, profile, warm, n_steps, hp_over=None, oracle_dtype=torch.float32, engine_kw=None):
+    """UN-SYNCED trajectory: engine and oracle start from the same weights and then each follows its OWN Adam
+    trajectory for n_steps (no state reload) - this is what tells whether the narrower backward GEMMs (single-pass
+    TF32 vs the reference's fp32) bend the loss curve.  Returns per-step losses of both and their relative gap."""
+    pb = make_problem(name, profile=profile, **(hp_over or {}))
+    hp = pb.hp
+    if warm:
+        warm_state(pb, warm)
+    eng = make_engine(pb, **(engine_kw or {}))
+    orc = make_oracle(pb, oracle_dtype)
+    logical = pb.layout.init_logical(hp.init_seed)
+    eng.set_params(logical)
+    orc.set_params(logical)
+    it = pb.input_fn()
+    K = hp.train_total_negative_samples
+    steps = []
+    for step in range(1, n_steps + 1):
+        feats, labels = it.get_next()
+        buf = pb.clicked_items_state.get_recent_clicks_buffer().copy()
+        pop = pb.clicked_items_state.get_articles_recent_pop_norm().copy()
+        out = eng.train_step(feats, labels, buf, pop)
+        allc = np.concatenate([feats['item_clicked'], labels['label_last_item']], axis=1)
+        neg_ref = sampler_ref.sample_negatives(allc, buf, K, hp.train_negative_samples_from_buffer, hp.sampler_seed, step)
+        o, _ = orc.train_step(feats, labels, neg_ref, buf, pop)
+        ref = float(o['total_loss'])
+        steps.append({'step': step, 'gpu': out['total_loss'], 'ref': ref, 'rel': abs(out['total_loss'] - ref) / abs(ref),
+                      'neg_equal': bool(np.array_equal(out['negatives'].cpu().numpy(), neg_ref))})
+        items, ts = batch_clicks_for_state_update(feats['item_clicked'], feats['event_timestamp'], labels['label_last_item'])
+        pb.clicked_items_state.update_items_state(items, ts)
+    p_gpu, p_ref = eng.get_params(), orc.get_params()
+    drift = max(float(np.abs(p_gpu[k] - p_ref[k]).max()) for k in p_ref)
+    return {'case': name, 'steps': steps, 'max_rel': max(s['rel'] for s in steps), 'param_drift_abs_max': drift,
+            'lr': hp.learning_rate}
 
 
 def main():

@@ -30,9 +30,11 @@ __device__ __forceinline__ float normalize(float x, const float* st) {
   return __fsub_rn(__fmul_rn(scaled, 2.0f), 1.0f);
 }
 
-__device__ __forceinline__ int row_group(int64_t r, int64_t n_input, int64_t n_cand) {
+// statistics group of a row: 0 clicked (input) rows, 1 positives, 2 negatives.  n_cand > 0: candidate rows come in
+// groups of n_cand, positive first; n_cand == 0: rows [n_input, n_input + n_positive) are the positives
+__device__ __forceinline__ int row_group(int64_t r, int64_t n_input, int64_t n_cand, int64_t n_positive = 0) {
   if (r < n_input) return 0;
-  if (n_cand <= 0) return 2;
+  if (n_cand <= 0) return r < n_input + n_positive ? 1 : 2;
   return ((r - n_input) % n_cand) == 0 ? 1 : 2;
 }
 
@@ -108,6 +110,8 @@ struct GatherArgs {
   const int64_t* created_at_ts; const float* pop_norm;
   float log_base_recency, log_base_novelty;
   int row_ld, n_narrow_blocks, period, n_col_groups;   // n_col_groups = ceil(narrow columns / 32)
+  int n_positive;                 // n_cand == 0 layout: rows [n_input, n_input + n_positive) are positives
+  int n_full, ctx_col0;           // rows >= n_full carry item features only: their columns >= ctx_col0 are written as 0
 };
 
 __global__ void __launch_bounds__(128)
@@ -266,7 +270,8 @@ gather_features_kernel(const __grid_constant__ GatherArgs A, const GatherDesc* _
       scale = -(1.0f / logf(A.log_base_novelty));
     }
     const float raw = __fmul_rn(logf(x), scale);               // == recency_raw / novelty_raw bit for bit
-    const int g = rr < n_input ? 0 : (n_cand <= 0 ? 2 : (((unsigned)(rr - n_input) % (unsigned)n_cand) == 0 ? 1 : 2));
+    const int g = rr < n_input ? 0 : (n_cand <= 0 ? (rr < n_input + A.n_positive ? 1 : 2)
+                                                  : (((unsigned)(rr - n_input) % (unsigned)n_cand) == 0 ? 1 : 2));
     c_norm = normalize(raw, A.stats + 8 * g + 4 * role);
   }
   const int src_lane = (unsigned)nd_z >> 24;
@@ -284,7 +289,8 @@ gather_features_kernel(const __grid_constant__ GatherArgs A, const GatherDesc* _
       mine = my_mode == SM_NUM_AT_ITEM ? as_num : mine;
       const int val = __shfl_sync(0xffffffffu, mine, src_lane);
       const float raw = narrow_raw(nd_z, nd_a, nd_c, nd_l, A.ebase, val);
-      if (kind != CK_NONE) ocol[(int64_t)k * A.row_ld] = raw * nd_g + nd_b;
+      const bool item_only = (base + k >= A.n_full) && ((nd_z & 0xffff) >= A.ctx_col0);    // no context on this row
+      if (kind != CK_NONE) ocol[(int64_t)k * A.row_ld] = item_only ? 0.f : raw * nd_g + nd_b;
     }
   }
 }
@@ -298,6 +304,7 @@ constexpr int BWD_THREADS = 256;
 __global__ void __launch_bounds__(BWD_THREADS)
 gather_features_bwd_kernel(const __grid_constant__ nar_feature_plan P, const int32_t* __restrict__ row_pos,
                            const int64_t* __restrict__ row_item, int64_t n_rows, int64_t n_input, int64_t n_cand,
+                           int64_t n_positive, int64_t n_full, int ctx_col0,
                            const int64_t* __restrict__ event_ts, const int64_t* __restrict__ max_ts,
                            const float* __restrict__ d_out, float* __restrict__ d_gamma, float* __restrict__ d_beta) {
   __shared__ int64_t s_pos[BWD_ROWS], s_item[BWD_ROWS], s_ts[BWD_ROWS];
@@ -310,12 +317,15 @@ gather_features_bwd_kernel(const __grid_constant__ nar_feature_plan P, const int
     s_pos[threadIdx.x] = pos;
     s_item[threadIdx.x] = row_item[r];
     s_ts[threadIdx.x] = (r < n_input) ? event_ts[pos] : max_ts[0];
-    s_grp[threadIdx.x] = row_group(r, n_input, n_cand);
+    s_grp[threadIdx.x] = row_group(r, n_input, n_cand, n_positive);
   }
   __syncthreads();
+  // rows >= n_full carry item features only: their context columns (>= ctx_col0) hold no gradient
+  const int nr_ctx = (int)max((int64_t)0, min((int64_t)nr, n_full - r0));
   for (int c = threadIdx.x; c < P.row_ld; c += BWD_THREADS) {
     const int si = P.col_seg[c];
     if (si == 255) continue;
+    const int nr = c >= ctx_col0 ? nr_ctx : (int)min((int64_t)BWD_ROWS, n_rows - r0);
     const nar_segment& sg = P.seg[si];
     const int j = c - sg.col;
     const float gam = P.gamma[c];
@@ -529,8 +539,56 @@ build_rows_kernel(const int32_t* __restrict__ pos_idx, int64_t L, const int64_t*
   }
 }
 
+// Base rows of the per-unique-id CAR layer 1 (engine.cu): [0,L) clicked items, [L,2L) positives, then one row per
+// entry of the step's unique-negative table (U = table capacity + 1: unused entries and the last "padding negative"
+// slot hold item 0; their context columns are written as 0).  Also fills the inverse map used by the deterministic
+// backward segment sum: Mt[u][l] = k+1 when position l drew unique item u as its k-th negative (a click's non-padding
+// negatives are distinct, so a (u, l) cell has at most one writer).  Mt must be zero on entry.
+__global__ void __launch_bounds__(256)
+build_base_rows_kernel(const int32_t* __restrict__ pos_idx, int64_t L, const int64_t* __restrict__ item_clicked,
+                       const int64_t* __restrict__ label_next, const int64_t* __restrict__ uitems,
+                       const int32_t* __restrict__ n_unique_p, int64_t U, const int32_t* __restrict__ neg_uidx, int64_t K,
+                       int32_t* __restrict__ base_pos, int64_t* __restrict__ base_item, uint16_t* __restrict__ Mt,
+                       int64_t ld_mt) {
+  const int64_t n_base = 2 * L + U, total = n_base + L * K;
+  const int n_unique = n_unique_p[0];
+  const int32_t pos0 = pos_idx[0];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < n_base) {
+      int32_t pos; int64_t item;
+      if (i < L) { pos = pos_idx[i]; item = item_clicked[pos]; }
+      else if (i < 2 * L) { pos = pos_idx[i - L]; item = label_next[pos]; }
+      else { const int64_t u = i - 2 * L; pos = pos0; item = u < n_unique ? uitems[u] : 0; }
+      base_pos[i] = pos; base_item[i] = item;
+    } else {
+      const int64_t e = i - n_base, l = e / K, k = e - l * K;
+      const int32_t u = neg_uidx[(int64_t)pos_idx[l] * K + k];
+      // the padding slot U-1 may be drawn several times by one click (trailing id-0 negatives): its rows are found
+      // by scanning neg_uidx instead (car_segsum_kernel), so it has no cell here
+      if (u >= 0 && u < U - 1) Mt[(int64_t)u * ld_mt + l] = (uint16_t)(k + 1);
+    }
+  }
+}
+
 }  // namespace feat
 }  // namespace nar
+
+extern "C" int nar_build_base_rows(const int32_t* pos_idx, int64_t L, const int64_t* item_clicked, const int64_t* label_next_item,
+                                   const int64_t* unique_items, const int32_t* n_unique, int64_t U, const int32_t* neg_uidx,
+                                   int64_t K, int32_t* base_pos, int64_t* base_item, uint16_t* Mt, int64_t ld_mt, void* stream) {
+  if (!pos_idx || !item_clicked || !label_next_item || !unique_items || !n_unique || !neg_uidx || !base_pos || !base_item || !Mt)
+    return NAR_ERR_INVALID;
+  if (K <= 0 || K >= 65535 || U <= 0 || ld_mt < L) return NAR_ERR_INVALID;
+  if (L <= 0) return NAR_OK;
+  NAR_CHECK_CUDA(cudaMemsetAsync(Mt, 0, (size_t)U * (size_t)ld_mt * sizeof(uint16_t), as_stream(stream)));
+  const int64_t total = 2 * L + U + L * K;
+  int64_t g = (total + 255) / 256; if (g > 148 * 8) g = 148 * 8;
+  nar::feat::build_base_rows_kernel<<<(unsigned)g, 256, 0, as_stream(stream)>>>(pos_idx, L, item_clicked, label_next_item,
+                                                                              unique_items, n_unique, U, neg_uidx, K,
+                                                                              base_pos, base_item, Mt, ld_mt);
+  NAR_LAUNCH_CHECK();
+  return NAR_OK;
+}
 
 extern "C" int nar_build_rows(const int32_t* pos_idx, int64_t L, const int64_t* item_clicked, const int64_t* label_next_item,
                               const int64_t* negatives, int64_t K, int32_t* row_pos, int64_t* row_item, void* stream) {
@@ -544,9 +602,11 @@ extern "C" int nar_build_rows(const int32_t* pos_idx, int64_t L, const int64_t* 
 }
 
 extern "C" int nar_gather_features(nar_ctx* ctx, const nar_feature_plan* plan, const int32_t* row_pos,
-                                   const int64_t* row_item, int64_t n_rows, int64_t n_input, int64_t n_cand,
+                                   const int64_t* row_item, const nar_row_layout* rows,
                                    const int64_t* event_timestamp, const int64_t* max_ts, float* out, void* stream) {
-  if (!ctx || !plan || !row_pos || !row_item || !out || !max_ts) return NAR_ERR_INVALID;
+  if (!ctx || !plan || !row_pos || !row_item || !out || !max_ts || !rows) return NAR_ERR_INVALID;
+  const int64_t n_rows = rows->n_rows, n_input = rows->n_input, n_cand = rows->n_cand;
+  if (n_cand < 0 || n_input < 0 || rows->n_positive < 0) return NAR_ERR_INVALID;
   if (plan->n_segments > NAR_MAX_SEGMENTS) return NAR_ERR_INVALID;
   if (n_rows <= 0) return NAR_OK;
   if (!ctx || !ctx->gather_desc) return NAR_ERR_INVALID;
@@ -616,6 +676,9 @@ extern "C" int nar_gather_features(nar_ctx* ctx, const nar_feature_plan* plan, c
   A.log_base_recency = plan->log_base_recency; A.log_base_novelty = plan->log_base_novelty;
   A.row_ld = plan->row_ld;
   A.ebase = e_lo; A.ntail = n_tail;
+  A.n_positive = (int)rows->n_positive;
+  A.n_full = rows->n_full < n_rows ? (int)(rows->n_full < 0 ? 0 : rows->n_full) : (int)n_rows;
+  A.ctx_col0 = (int)rows->ctx_col0;
   const nar::feat::GatherDesc* D = static_cast<const nar::feat::GatherDesc*>(ctx->gather_desc);
   // narrow CTAs first (longer running): one warp per (chunk of 8 rows, 32 columns); then one wide CTA per 8 rows
   const int64_t n_chunks = (n_rows + nar::feat::GATHER_CHUNK - 1) / nar::feat::GATHER_CHUNK;
@@ -638,14 +701,17 @@ extern "C" int nar_gather_features(nar_ctx* ctx, const nar_feature_plan* plan, c
 }
 
 extern "C" int nar_gather_features_bwd(nar_ctx* ctx, const nar_feature_plan* plan, const int32_t* row_pos,
-                                       const int64_t* row_item, int64_t n_rows, int64_t n_input, int64_t n_cand,
+                                       const int64_t* row_item, const nar_row_layout* rows,
                                        const int64_t* event_timestamp, const int64_t* max_ts, const float* d_out,
                                        float* d_gamma, float* d_beta, void* stream) {
-  if (!ctx || !plan || !row_pos || !row_item || !d_out || !d_gamma || !d_beta) return NAR_ERR_INVALID;
+  if (!ctx || !plan || !row_pos || !row_item || !d_out || !d_gamma || !d_beta || !rows) return NAR_ERR_INVALID;
+  const int64_t n_rows = rows->n_rows, n_input = rows->n_input, n_cand = rows->n_cand;
   if (n_rows <= 0) return NAR_OK;
+  const int64_t n_full = rows->n_full < n_rows ? (rows->n_full < 0 ? 0 : rows->n_full) : n_rows;
   const unsigned grid = (unsigned)((n_rows + nar::feat::BWD_ROWS - 1) / nar::feat::BWD_ROWS);
   nar::feat::gather_features_bwd_kernel<<<grid, nar::feat::BWD_THREADS, 0, as_stream(stream)>>>(
-      *plan, row_pos, row_item, n_rows, n_input, n_cand, event_timestamp, max_ts, d_out, d_gamma, d_beta);
+      *plan, row_pos, row_item, n_rows, n_input, n_cand, rows->n_positive, n_full, (int)rows->ctx_col0, event_timestamp, max_ts,
+      d_out, d_gamma, d_beta);
   NAR_LAUNCH_CHECK();
   return NAR_OK;
 }

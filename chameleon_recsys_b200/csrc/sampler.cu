@@ -259,15 +259,18 @@ pool_kernel(const int64_t* __restrict__ all_items, int64_t NB, const int64_t* __
 
 __global__ void __launch_bounds__(CLICK_THREADS)
 click_kernel(const int64_t* __restrict__ all_items, int64_t T1, int64_t sess0, int64_t K, uint64_t seed, uint32_t step,
-             PoolWs ws, int64_t* __restrict__ out) {
+             PoolWs ws, int64_t* __restrict__ out, int32_t* __restrict__ out_uidx, int32_t zero_slot) {
   extern __shared__ uint64_t ukey[];               // [next_pow2(n_unique)]
   const int64_t T = T1 - 1;
   const int64_t b = blockIdx.x / T, p = blockIdx.x % T;
   const int64_t* sess = all_items + (sess0 + b) * T1;
   int64_t* o = out + ((int64_t)blockIdx.x) * K;
+  // optional second output: the index of each negative in the pool's sorted unique-item table (ws.uitems), or
+  // zero_slot for a padding negative (id 0) - what the per-unique-id CAR layer 1 is keyed by
+  int32_t* ou = out_uidx ? out_uidx + ((int64_t)blockIdx.x) * K : nullptr;
   const int n_pool = ws.counters[0], n_unique = ws.counters[1];
   if (sess[p] == 0 || n_unique == 0) {
-    for (int64_t r = threadIdx.x; r < K; r += CLICK_THREADS) o[r] = 0;
+    for (int64_t r = threadIdx.x; r < K; r += CLICK_THREADS) { o[r] = 0; if (ou) ou[r] = zero_slot; }
     return;
   }
   const uint32_t np2 = next_pow2((uint32_t)n_unique);
@@ -304,6 +307,7 @@ click_kernel(const int64_t* __restrict__ all_items, int64_t T1, int64_t sess0, i
   for (int64_t r = threadIdx.x; r < K; r += CLICK_THREADS) {
     const uint64_t key = r < np2 ? ukey[r] : KEY_MAX;
     o[r] = key == KEY_MAX ? 0 : ws.pool_item[(int)(key & 0xFFFFFFFFull)];
+    if (ou) ou[r] = key == KEY_MAX ? zero_slot : ws.pool_uidx[(int)(key & 0xFFFFFFFFull)];
   }
 }
 
@@ -338,6 +342,15 @@ extern "C" int nar_sample_negatives(nar_ctx* ctx, const int64_t* all_items_globa
                                     int64_t B, const int64_t* buffer, int64_t buf_len, int64_t K, int64_t n_from_buffer,
                                     uint64_t seed, uint32_t step, int64_t* out, void* workspace, int64_t workspace_bytes,
                                     void* stream) {
+  return nar_sample_negatives_uidx(ctx, all_items_global, Bg, T1, sess0, B, buffer, buf_len, K, n_from_buffer, seed, step, out,
+                                   nullptr, nullptr, nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" int nar_sample_negatives_uidx(nar_ctx* ctx, const int64_t* all_items_global, int64_t Bg, int64_t T1, int64_t sess0,
+                                         int64_t B, const int64_t* buffer, int64_t buf_len, int64_t K, int64_t n_from_buffer,
+                                         uint64_t seed, uint32_t step, int64_t* out, int32_t* out_uidx,
+                                         const int64_t** unique_items, const int32_t** n_unique, void* workspace,
+                                         int64_t workspace_bytes, void* stream) {
   using namespace nar::sampler;
   if (!ctx || !all_items_global || !buffer || !out || !workspace) return NAR_ERR_INVALID;
   if (T1 < 2 || K <= 0 || B < 0 || sess0 < 0 || sess0 + B > Bg) return NAR_ERR_INVALID;
@@ -359,8 +372,11 @@ extern "C" int nar_sample_negatives(nar_ctx* ctx, const int64_t* all_items_globa
   pool_kernel<<<1, POOL_THREADS, smem, st>>>(all_items_global, Bg * T1, buffer, buf_len, n_from_buffer, cap, seed, step, ws);
   NAR_LAUNCH_CHECK();
   if (B > 0) {
-    click_kernel<<<(unsigned)(B * (T1 - 1)), CLICK_THREADS, smem, st>>>(all_items_global, T1, sess0, K, seed, step, ws, out);
+    click_kernel<<<(unsigned)(B * (T1 - 1)), CLICK_THREADS, smem, st>>>(all_items_global, T1, sess0, K, seed, step, ws, out,
+                                                                         out_uidx, (int32_t)cap);
     NAR_LAUNCH_CHECK();
   }
+  if (unique_items) *unique_items = ws.uitems;
+  if (n_unique) *n_unique = ws.counters + 1;
   return NAR_OK;
 }

@@ -134,7 +134,11 @@ class FeaturePlan:
             segs.append(Segment(SEG_NOVELTY, 'novelty', 1, col)); col += 1
         self.segments = segs
         self.F = col
-        # ---- internal (HBM) order: wide segments first at 4-float aligned offsets
+        # ---- internal (HBM) order: ITEM side first - the wide segments at 4-float aligned offsets, then the narrow
+        # item segments (metadata, recency, novelty) - and the user-CONTEXT segments last, starting at the 4-float
+        # aligned column ctx_col0: the item half [0, ctx_col0) and the context half [ctx_col0, Fp) of a row (and the
+        # matching row blocks of W1) can then be used as separate, TMA-aligned GEMM operands (per-unique-id CAR layer 1)
+        ctx_kinds = (SEG_CTX_OHE, SEG_CTX_EMBED, SEG_CTX_NUM, SEG_CTX_ZERO)
         icol = 0
         for s in segs:
             if s.kind in (SEG_ACR, SEG_ITEM_EMB):
@@ -142,7 +146,13 @@ class FeaturePlan:
                 s.int_col = icol
                 icol += s.width
         for s in segs:
-            if s.kind not in (SEG_ACR, SEG_ITEM_EMB):
+            if s.kind not in (SEG_ACR, SEG_ITEM_EMB) and s.kind not in ctx_kinds:
+                s.int_col = icol
+                icol += s.width
+        icol = round_up(icol, 4)
+        self.ctx_col0 = icol
+        for s in segs:
+            if s.kind in ctx_kinds:
                 s.int_col = icol
                 icol += s.width
         self.F_int = icol

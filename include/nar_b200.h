@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define NAR_ABI_VERSION 1
+#define NAR_ABI_VERSION 2
 
 typedef enum {
   NAR_OK = 0,
@@ -89,20 +89,29 @@ typedef struct {
   uint8_t col_seg[NAR_MAX_COLS];
 } nar_feature_plan;
 
+/* Which rows a row list holds.  Rows [0, n_input) are clicked items (reference timestamp = event_timestamp[row_pos],
+ * normalisation statistics group 0, nar_model.py:328); the others use max_ts (:343, :356) and are either
+ *   n_cand > 0 : groups of n_cand rows per position, the positive first (group 1) then its negatives (group 2), or
+ *   n_cand == 0: n_positive positive rows (group 1) followed by negative rows (group 2) - the base rows of the
+ *                per-unique-id CAR layer 1 (nar_build_base_rows).
+ * Rows >= n_full carry ITEM features only: their context columns (internal column >= ctx_col0) are written as 0 and
+ * skipped by the backward pass.  n_full >= n_rows: every row is a full row.                                         */
+typedef struct {
+  int64_t n_rows, n_input, n_cand, n_positive, n_full, ctx_col0;
+} nar_row_layout;
+
 /* rows: row_pos[r] = flat index b*T+t of the position that owns row r (context features,
- * reference timestamp), row_item[r] = article id, row_ts_kind: rows < n_input use
- * event_timestamp[row_pos], the others use max_ts (nar_model.py:328,:343,:356).            */
+ * reference timestamp), row_item[r] = article id.                                           */
 int nar_gather_features(nar_ctx* ctx, const nar_feature_plan* plan /*host*/,
-                        const int32_t* row_pos, const int64_t* row_item, int64_t n_rows, int64_t n_input,
-                        int64_t n_cand /* candidate rows come in groups of n_cand: positive first, then negatives */,
+                        const int32_t* row_pos, const int64_t* row_item, const nar_row_layout* rows /*host*/,
                         const int64_t* event_timestamp /*[B*T]*/, const int64_t* max_ts /*[1]*/,
                         float* out /*[n_rows,row_ld]*/, void* stream);
 
 /* backward of the same: d_gamma += sum_r dX*raw, d_beta += sum_r dX, trainable embedding
  * grads += dX*gamma scattered by id (IndexedSlices scatter-add, nar_model.py:918/:741).     */
 int nar_gather_features_bwd(nar_ctx* ctx, const nar_feature_plan* plan /*host*/,
-                            const int32_t* row_pos, const int64_t* row_item, int64_t n_rows, int64_t n_input,
-                            int64_t n_cand, const int64_t* event_timestamp, const int64_t* max_ts,
+                            const int32_t* row_pos, const int64_t* row_item, const nar_row_layout* rows /*host*/,
+                            const int64_t* event_timestamp, const int64_t* max_ts,
                             const float* d_out /*[n_rows,row_ld]*/, float* d_gamma, float* d_beta, void* stream);
 
 /* row lists of one step.  The L valid positions (pos_idx[l] = b*T+t, session-major) produce
@@ -111,6 +120,16 @@ int nar_gather_features_bwd(nar_ctx* ctx, const nar_feature_plan* plan /*host*/,
  * negatives (:356).                                                                        */
 int nar_build_rows(const int32_t* pos_idx, int64_t L, const int64_t* item_clicked, const int64_t* label_next_item,
                    const int64_t* negatives /*[B*T,K]*/, int64_t K, int32_t* row_pos, int64_t* row_item, void* stream);
+
+/* base rows of the per-unique-id CAR layer 1 (csrc/car.cu): n_base = 2L + U rows = the L clicked items, the L positives,
+ * then one ITEM-ONLY row per entry of the step's unique-negative table (unique_items / n_unique as returned by
+ * nar_sample_negatives_uidx; U = table capacity K*20 plus one trailing slot for the padding negative, id 0).  Also
+ * writes the inverse map Mt [U, ld_mt] uint16: Mt[u][l] = k+1 when position l drew unique entry u as its k-th
+ * negative (neg_uidx [B*T, K]), 0 otherwise - what nar_car_segsum walks to sum gradients in a fixed order.         */
+int nar_build_base_rows(const int32_t* pos_idx, int64_t L, const int64_t* item_clicked, const int64_t* label_next_item,
+                        const int64_t* unique_items, const int32_t* n_unique /*[1] device*/, int64_t U,
+                        const int32_t* neg_uidx, int64_t K, int32_t* base_pos /*[2L+U]*/, int64_t* base_item /*[2L+U]*/,
+                        uint16_t* Mt, int64_t ld_mt, void* stream);
 
 /* normalisation statistics of recency / novelty over the first n_norm nonzero buffer entries
  * (nar_model.py:1062-1089, :1150-1193, :1011-1039).  stats[g][8], g = 0 input / 1 positive /
@@ -176,6 +195,24 @@ int nar_sample_negatives(nar_ctx* ctx, const int64_t* all_items_global, int64_t 
                          int64_t sess0, int64_t B, const int64_t* buffer, int64_t buf_len,
                          int64_t K, int64_t n_from_buffer, uint64_t seed, uint32_t step,
                          int64_t* out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* the same, additionally returning for every negative its index in the pool's sorted unique-item table
+ * (out_uidx [B,T1-1,K] int32; K*20 = the padding slot for an id-0 negative) and device pointers to that table /
+ * its length inside `workspace` (valid until the next call with the same workspace).                              */
+int nar_sample_negatives_uidx(nar_ctx* ctx, const int64_t* all_items_global, int64_t Bg, int64_t T1,
+                              int64_t sess0, int64_t B, const int64_t* buffer, int64_t buf_len,
+                              int64_t K, int64_t n_from_buffer, uint64_t seed, uint32_t step,
+                              int64_t* out, int32_t* out_uidx /*or NULL*/, const int64_t** unique_items /*host, out*/,
+                              const int32_t** n_unique /*host, out*/, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- per-unique-id CAR layer 1 (nar_model.py:343-405; see csrc/car.cu): pre-activation of candidate (l, j) =
+ *      j == 0 ? PP[l] : PC[l] + PI[neg_uidx[pos_idx[l], j-1]]; H1c [L*(1+K), C] = act(pre).                        */
+int nar_car_combine(const float* PP /*[L,C]*/, const float* PC /*[L,C]*/, const float* PI /*[U,C]*/,
+                    const int32_t* pos_idx, const int32_t* neg_uidx, int64_t L, int64_t K, int64_t C, int act,
+                    float* H1c, void* stream);
+/* backward: dPP[l] = dH1c[l,0]; dPC[l] = sum_k dH1c[l,1+k]; dPI[u] = sum of the rows that drew u (fixed order).   */
+int nar_car_segsum(const float* dH1c, int64_t L, int64_t K, int64_t C, int64_t U, const uint16_t* Mt, int64_t ld_mt,
+                   const int32_t* pos_idx, const int32_t* neg_uidx, float* dPP, float* dPC, float* dPI, void* stream);
 
 /* ---- scorer + loss (replaces tf.multiply + matching_dense_layer_1..4 :478-500, softmax
  *      :515, log :660, masked mean :664).                                                  */

@@ -312,9 +312,8 @@ def run_ours(args):
         """step i on the main stream; the weight-independent front of step i+1 (sampler, row lists, statistics)
         is queued on the side stream right behind it (the reference prefetches its next batch the same way)"""
         st = staged[i]
-        eng.grads.zero_()
-        eng.step(st, train=True)
-        eng.apply_gradients()
+        eng.step(st, train=True)             # ONE C call: forward + backward, every launch sequenced in libnar_b200
+        eng.apply_gradients(st)              # (NCCL sum of the gradients when world > 1) + TF-Adam
         if eng.use_side_stream and i + 1 < len(staged):
             eng.prepare(staged[i + 1], eng.global_step + 1, stream=side)
 
@@ -323,10 +322,14 @@ def run_ours(args):
     depth = int(os.environ.get('NAR_BENCH_DEPTH', '2'))
     done = {}
 
+    enq = [0.0]
+
     def bounded_step(i):
         if depth > 0 and (i - depth) in done:
             done.pop(i - depth).synchronize()
+        t0 = time.perf_counter()
         dev_step(i)
+        enq[0] += time.perf_counter() - t0      # host time spent queueing the step (the wait above is not part of it)
         if depth > 0:
             ev = torch.cuda.Event()
             ev.record()
@@ -338,16 +341,18 @@ def run_ours(args):
     barrier()
     if rank == 0:
         sampler.start()
-    l0 = ops.LAUNCHES
+    l0 = eng.launches + ops.LAUNCHES
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     t_host0 = time.perf_counter()
+    enq[0] = 0.0
     for i in range(args.warmup, n_total):
         bounded_step(i)
     e1.record()
-    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps
+    host_loop_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps
+    host_enqueue_ms = enq[0] * 1e3 / args.steps
     barrier()
-    launches = ops.LAUNCHES - l0
+    launches = eng.launches + ops.LAUNCHES - l0
     ms = torch.tensor([e0.elapsed_time(e1)], device='cuda')
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -419,7 +424,7 @@ def run_ours(args):
 
     line = {'metric': 'NAR train interactions/sec', 'value': value, 'unit': 'interactions/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (tcgen05 kind::tf32: 3xTF32 forward, TF32 backward; fp32 accumulate)',
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (tcgen05 kind::tf32: 3xTF32 forward, TF32 backward; fp32 accumulate)', 'dedup_car_layer1': bool(eng.dedup),
             'data': 'synthetic', 'config': workload_config(pb, args, gb),
             'interactions_per_step': n_int / args.steps,
             'e2e': {'value': e2e_value, 'unit': 'interactions/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 16,
@@ -427,7 +432,8 @@ def run_ours(args):
                     'runs_ms_per_step': [r['ms'] / args.steps for r in e2e_runs], 'policy': 'median of three K-step regions',
                     'api': 'Estimator.train(input_fn) -> nar_module_model_fn -> NARModuleModel.train + ItemsStateUpdaterHook'},
             'gpu_launches': launches, 'gpu_launches_per_step': launches / args.steps,
-            'host_enqueue_ms_per_step': host_enqueue_ms, 'host_run_ahead_steps': depth,
+            'host_enqueue_ms_per_step': host_enqueue_ms, 'host_loop_ms_per_step_incl_waiting_for_the_gpu': host_loop_ms,
+            'host_run_ahead_steps': depth,
             'roofline': roof, 'roofline_gather': roof_g, 'clocks': clocks}
     if cpu:
         line['cpu_baseline'] = cpu
@@ -453,14 +459,12 @@ def kernel_rooflines(eng, st, hbm_peak, tf_peak, peak_src):
     import torch
     from chameleon_recsys_b200 import ops
     from chameleon_recsys_b200._lib import ACT_TANH
-    eng.grads.zero_()
     eng.step(st, train=False, keep=True)
     L, K = st['L'], eng.K
     R = L + L * (K + 1)
     plan = eng.plan
-    planc = eng._plan_c(st)
+    planc = eng.feature_plan_c(st)
     t = st['t']
-    X = eng._buf('X', R, plan.Fp)
     row_pos, row_item = eng.last['row_pos'], eng.last['row_item']
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')
 
@@ -476,7 +480,12 @@ def kernel_rooflines(eng, st, hbm_peak, tf_peak, peak_src):
             ts.append(a.elapsed_time(b))
         return float(np.mean(ts))
 
-    ms_g = timeit(lambda: ops.gather_features(planc, row_pos, row_item, R, L, K + 1, t['event_ts'], t['max_ts'], X))
+    # ---- embedding gather.  (a) the bulk form SURVEY 8(d) defines the byte count on: one feature row per (position,
+    # candidate) pair, R = L*(2+K) rows; (b) what the step actually launches since the per-unique-id CAR layer 1: the
+    # 2L + U base rows (every distinct negative id once) - 13x fewer bytes, a launch-latency sized kernel.
+    Xfull = torch.empty(R, plan.Fp, device='cuda')
+    rows_full = ops.row_layout(R, L, K + 1, ctx_col0=plan.ctx_col0)
+    ms_g = timeit(lambda: ops.gather_features(planc, row_pos, row_item, rows_full, t['event_ts'], t['max_ts'], Xfull))
     zed = torch.zeros(4, device='cuda')
     ms_0 = timeit(lambda: zed.zero_())            # what an (almost) empty kernel costs between the same two events
     E = plan.acr_dim if plan.use_acr else 0
@@ -491,18 +500,33 @@ def kernel_rooflines(eng, st, hbm_peak, tf_peak, peak_src):
               'achieved_incl_all_columns': actual / (ms_g * 1e-3) / 1e9,
               'event_pair_overhead_us': ms_0 * 1e3,
               'frac_net_of_event_overhead': gbytes / (max(ms_g - ms_0, 1e-6) * 1e-3) / 1e9 / hbm_peak,
-              'note': 'one launch per step; timed alone between two CUDA events with the L2 flushed (256 MB memset) before every '
-                      'iteration, so `us` includes the event-pair overhead reported next to it and the write-back of the '
-                      "flush's dirty lines; algorithmic bytes count only the ACR + item-embedding rows (SURVEY 8d), the kernel "
-                      'also writes the %d context / metadata / recency / novelty / padding columns of every row' % (plan.Fp - E - Di)}
-    # dominant kernel: CAR layer 2 forward GEMM [R,C]x[C,C], 3xTF32
-    H1 = eng._buf('H1', R, eng.C); Eb = eng._buf('E', R, eng.C)
-    ms_m = timeit(lambda: eng._fwd(H1, 'W2', 'b2', Eb, R, ACT_TANH), iters=10)
+              'note': 'bulk form: one feature row per (position, candidate) pair as SURVEY 8(d) counts it; timed alone between '
+                      'two CUDA events with the L2 flushed (256 MB memset) before every iteration, so `us` includes the '
+                      'event-pair overhead reported next to it; algorithmic bytes count only the ACR + item-embedding rows, '
+                      'the kernel also writes the %d context / metadata / recency / novelty / padding columns of every row'
+                      % (plan.Fp - E - Di)}
+    if eng.dedup:
+        nb = 2 * L + K * 20 + 1
+        rows_b = ops.row_layout(nb, L, 0, n_positive=L, n_full=2 * L, ctx_col0=plan.ctx_col0)
+        bp, bi = eng.buffer(st, 'base_pos').view(-1), eng.buffer(st, 'base_item').view(-1)
+        Xb = eng.buffer(st, 'X')
+        ms_b = timeit(lambda: ops.gather_features(planc, bp, bi, rows_b, t['event_ts'], t['max_ts'], Xb))
+        bbytes = nb * ((E + Di) * 4 * 2 + 8)
+        roof_g['in_step'] = {'rows': nb, 'us': ms_b * 1e3, 'algorithmic_bytes': bbytes,
+                             'achieved': bbytes / (ms_b * 1e-3) / 1e9, 'frac': bbytes / (ms_b * 1e-3) / 1e9 / hbm_peak,
+                             'bytes_vs_bulk': bbytes / gbytes,
+                             'note': 'the launch the training step makes: clicked + positive rows and ONE row per distinct '
+                                     'negative id (exact per-unique-id CAR layer 1); %.1fx fewer bytes than the bulk form' % (gbytes / bbytes)}
+    # ---- dominant kernel: CAR layer 2 forward GEMM [R,C]x[C,C], 3xTF32
+    H1, Eb = eng.buffer(st, 'H1'), eng.buffer(st, 'E')
+    W2, b2, W2lo = eng.view('W2'), eng.view('b2').view(-1), eng.view('W2', eng.params_lo)
+
+    def car2(prec):
+        ops.gemm(H1, W2, Eb, R, eng.C, eng.C, a_kmajor=True, b_kmajor=False, bias=b2, act=ACT_TANH, precision=prec,
+                 b_lo=W2lo if prec == 3 else None)
+    ms_m = timeit(lambda: car2(3), iters=10)
     flops = 2.0 * R * eng.C * eng.C
-    old = eng.fwd_prec
-    eng.fwd_prec = 1
-    ms_m1 = timeit(lambda: eng._fwd(H1, 'W2', 'b2', Eb, R, ACT_TANH), iters=10)
-    eng.fwd_prec = old
+    ms_m1 = timeit(lambda: car2(1), iters=10)
     roof = {'kernel': 'gemm_tf32_kernel<A K-major, B MN-major, 3xTF32 with the A split kept in tensor memory> '
                       '(CAR_representation layer 2 forward)', 'bound': 'tensor',
             'achieved': flops / (ms_m * 1e-3) / 1e12, 'peak': tf_peak, 'unit': 'TFLOP/s',

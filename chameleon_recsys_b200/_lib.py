@@ -38,6 +38,44 @@ class FeaturePlanC(C.Structure):
                 ('col_seg', C.c_uint8 * NAR_MAX_COLS)]
 
 
+class RowLayout(C.Structure):
+    _fields_ = [('n_rows', C.c_int64), ('n_input', C.c_int64), ('n_cand', C.c_int64), ('n_positive', C.c_int64),
+                ('n_full', C.c_int64), ('ctx_col0', C.c_int64)]
+
+
+NAR_MAX_LAYERS = 4
+
+
+class ModelCfg(C.Structure):
+    _fields_ = [('num_items', C.c_int64), ('C', C.c_int64), ('Hp', C.c_int64), ('Fp', C.c_int64), ('ctx_col0', C.c_int64),
+                ('layers', C.c_int32), ('rnn_cell', C.c_int32), ('ranking', C.c_int32),
+                ('fwd_precision', C.c_int32), ('bwd_precision', C.c_int32), ('dedup', C.c_int32), ('use_aux_stream', C.c_int32),
+                ('K', C.c_int64), ('n_from_buffer', C.c_int64), ('buf_len', C.c_int64), ('n_norm', C.c_int64),
+                ('inv_temperature', C.c_float), ('reg_l2', C.c_float), ('lr', C.c_float), ('beta1', C.c_float),
+                ('beta2', C.c_float), ('eps', C.c_float),
+                ('sampler_seed', C.c_uint64), ('world', C.c_int32), ('rank', C.c_int32),
+                ('params', C.c_void_p), ('params_lo', C.c_void_p), ('grads', C.c_void_p), ('adam_m', C.c_void_p),
+                ('adam_v', C.c_void_p), ('n_params', C.c_int64), ('reg_end', C.c_int64),
+                ('off_W1', C.c_int64), ('off_b1', C.c_int64), ('off_W2', C.c_int64), ('off_b2', C.c_int64),
+                ('off_W3', C.c_int64), ('off_b3', C.c_int64), ('off_W4', C.c_int64), ('off_b4', C.c_int64),
+                ('off_gamma', C.c_int64), ('off_beta', C.c_int64),
+                ('off_M', C.c_int64 * 4), ('off_c', C.c_int64 * 4), ('ld_M', C.c_int64 * 4),
+                ('off_Wx', C.c_int64 * NAR_MAX_LAYERS), ('off_Wh', C.c_int64 * NAR_MAX_LAYERS), ('off_rb', C.c_int64 * NAR_MAX_LAYERS),
+                ('plan', FeaturePlanC)]
+
+
+class StepIO(C.Structure):
+    _fields_ = [('B', C.c_int64), ('Bg', C.c_int64), ('T', C.c_int64), ('sess0', C.c_int64), ('L', C.c_int64),
+                ('L_global', C.c_int64), ('L_cap', C.c_int64), ('global_step', C.c_int64),
+                ('sampler_step', C.c_uint32), ('train', C.c_int32),
+                ('all_items', C.c_void_p), ('event_ts', C.c_void_p), ('item_clicked', C.c_void_p), ('label_next', C.c_void_p),
+                ('buffer', C.c_void_p), ('max_ts', C.c_void_p), ('pop_norm', C.c_void_p),
+                ('ctx_int', C.c_void_p * NAR_MAX_SRC), ('ctx_float', C.c_void_p * NAR_MAX_SRC),
+                ('pos_idx', C.c_void_p), ('sess_off', C.c_void_p),
+                ('prep_ws', C.c_void_p), ('prep_ws_bytes', C.c_int64), ('ws', C.c_void_p), ('ws_bytes', C.c_int64),
+                ('loss', C.c_void_p)]
+
+
 class GemmEpilogue(C.Structure):
     _fields_ = [('bias', C.c_void_p), ('act', C.c_int32), ('dact', C.c_int32), ('aux', C.c_void_p),
                 ('ld_aux', C.c_int64), ('accumulate', C.c_int32), ('split_k', C.c_int32),
@@ -50,11 +88,26 @@ i64, i32, f32, vp, u64, u32 = C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_u
 
 _SIGNATURES = {
     'nar_abi_version': (C.c_int, []),
+    'nar_abi_struct_size': (C.c_int, [C.c_int]),
     'nar_status_string': (C.c_char_p, [C.c_int]),
     'nar_ctx_create': (C.c_int, [C.c_int, C.POINTER(vp)]),
     'nar_ctx_destroy': (C.c_int, [vp]),
-    'nar_gather_features': (C.c_int, [vp, C.POINTER(FeaturePlanC), vp, vp, i64, i64, i64, vp, vp, vp, vp]),
-    'nar_gather_features_bwd': (C.c_int, [vp, C.POINTER(FeaturePlanC), vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, vp]),
+    'nar_gather_features': (C.c_int, [vp, C.POINTER(FeaturePlanC), vp, vp, C.POINTER(RowLayout), vp, vp, vp, vp]),
+    'nar_gather_features_bwd': (C.c_int, [vp, C.POINTER(FeaturePlanC), vp, vp, C.POINTER(RowLayout), vp, vp, vp, vp, vp, vp]),
+    'nar_build_base_rows': (C.c_int, [vp, i64, vp, vp, vp, vp, i64, vp, i64, vp, vp, vp, i64, vp]),
+    'nar_sample_negatives_uidx': (C.c_int, [vp, vp, i64, i64, i64, i64, vp, i64, i64, i64, u64, u32, vp, vp,
+                                            C.POINTER(vp), C.POINTER(vp), vp, i64, vp]),
+    'nar_car_combine': (C.c_int, [vp, vp, vp, vp, vp, i64, i64, i64, C.c_int, vp, vp]),
+    'nar_car_segsum': (C.c_int, [vp, i64, i64, i64, i64, vp, i64, vp, vp, vp, vp, vp, vp]),
+    'nar_engine_create': (C.c_int, [vp, C.POINTER(ModelCfg), C.POINTER(vp)]),
+    'nar_engine_destroy': (C.c_int, [vp]),
+    'nar_engine_update_cfg': (C.c_int, [vp, C.POINTER(ModelCfg)]),
+    'nar_engine_workspace_bytes': (C.c_int, [vp, i64, i64, i64, i64, i32, C.POINTER(i64), C.POINTER(i64)]),
+    'nar_engine_prepare': (C.c_int, [vp, C.POINTER(StepIO), vp]),
+    'nar_engine_step': (C.c_int, [vp, C.POINTER(StepIO), vp]),
+    'nar_engine_apply': (C.c_int, [vp, C.POINTER(StepIO), vp]),
+    'nar_engine_buffer': (C.c_int, [vp, C.POINTER(StepIO), C.c_char_p, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)]),
+    'nar_engine_launch_count': (i64, [vp]),
     'nar_build_rows': (C.c_int, [vp, i64, vp, vp, vp, i64, vp, vp, vp]),
     'nar_feature_stats': (C.c_int, [vp, vp, i64, i64, vp, vp, vp, f32, f32, vp, vp, i64, i64, i64, vp, vp, vp]),
     'nar_gather_rows_f32': (C.c_int, [vp, i64, i64, C.c_int, vp, i64, vp, i64, vp]),
@@ -97,7 +150,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.nar_abi_version() != 1:
+    if lib.nar_abi_version() != 2:
         raise NarError('ABI version mismatch')
     _lib = lib
     return lib

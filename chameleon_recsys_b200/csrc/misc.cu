@@ -103,6 +103,18 @@ static unsigned grid_for(int64_t n, int per_block) {
 // ------------------------------------------------------------------ context
 extern "C" int nar_abi_version(void) { return NAR_ABI_VERSION; }
 
+extern "C" int nar_abi_struct_size(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(nar_feature_plan);
+    case 1: return (int)sizeof(nar_model_cfg);
+    case 2: return (int)sizeof(nar_step_io);
+    case 3: return (int)sizeof(nar_row_layout);
+    case 4: return (int)sizeof(nar_gemm_epilogue);
+    case 5: return (int)sizeof(nar_segment);
+  }
+  return -1;
+}
+
 extern "C" const char* nar_status_string(int status) {
   switch (status) {
     case NAR_OK: return "ok";

@@ -97,19 +97,23 @@ def scatter_add_rows(table: torch.Tensor, ids: torch.Tensor, src: torch.Tensor, 
                                        src.stride(0), _stream()), 'nar_scatter_add_rows_f32')
 
 
-def gather_features(plan: FeaturePlanC, row_pos, row_item, n_rows, n_input, n_cand, event_ts, max_ts, out):
+def row_layout(n_rows, n_input, n_cand, n_positive=0, n_full=None, ctx_col0=0) -> _lib.RowLayout:
+    return _lib.RowLayout(n_rows, n_input, n_cand, n_positive, n_rows if n_full is None else n_full, ctx_col0)
+
+
+def gather_features(plan: FeaturePlanC, row_pos, row_item, rows: _lib.RowLayout, event_ts, max_ts, out):
     global LAUNCHES
     LAUNCHES += 1
     ctx = context()
-    check(ctx.lib.nar_gather_features(ctx.handle, C.byref(plan), _p(row_pos), _p(row_item), n_rows, n_input, n_cand,
+    check(ctx.lib.nar_gather_features(ctx.handle, C.byref(plan), _p(row_pos), _p(row_item), C.byref(rows),
                                       _p(event_ts), _p(max_ts), _p(out), _stream()), 'nar_gather_features')
 
 
-def gather_features_bwd(plan: FeaturePlanC, row_pos, row_item, n_rows, n_input, n_cand, event_ts, max_ts, d_out, d_gamma, d_beta):
+def gather_features_bwd(plan: FeaturePlanC, row_pos, row_item, rows: _lib.RowLayout, event_ts, max_ts, d_out, d_gamma, d_beta):
     global LAUNCHES
     LAUNCHES += 1
     ctx = context()
-    check(ctx.lib.nar_gather_features_bwd(ctx.handle, C.byref(plan), _p(row_pos), _p(row_item), n_rows, n_input, n_cand,
+    check(ctx.lib.nar_gather_features_bwd(ctx.handle, C.byref(plan), _p(row_pos), _p(row_item), C.byref(rows),
                                           _p(event_ts), _p(max_ts), _p(d_out), _p(d_gamma), _p(d_beta), _stream()),
           'nar_gather_features_bwd')
 
@@ -235,57 +239,3 @@ def tf32_lo(x, n, lo):
     global LAUNCHES
     LAUNCHES += 1
     check(_lib.load().nar_tf32_lo(_p(x), n, _p(lo), _stream()), 'nar_tf32_lo')
-
-
-# ---------------------------------------------------------------------------------------------------
-# optional per-op device timing (NAR_PROFILE=1): CUDA events around every wrapper call on the current
-# stream; `profile_report()` aggregates.  Diagnostic only - it serialises nothing but adds event overhead.
-# ---------------------------------------------------------------------------------------------------
-import os as _os
-
-_PROFILE_EVENTS = []
-
-
-def _install_profiler():
-    import functools
-    g = globals()
-    names = ['gemm', 'gather_features', 'gather_features_bwd', 'build_rows', 'feature_stats', 'ugrnn_fwd', 'ugrnn_bwd',
-             'sample_negatives', 'mul_pred', 'mul_pred_bwd', 'score_softmax_ce', 'cosine_softmax_ce', 'colsum_add',
-             'act_bwd', 'l2_loss_add', 'transpose', 'adam_tf', 'tf32_lo']
-
-    def wrap(name, fn):
-        @functools.wraps(fn)
-        def timed(*a, **k):
-            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-            e0.record()
-            r = fn(*a, **k)
-            e1.record()
-            tag = name
-            if name == 'gemm':
-                tag = 'gemm[%s%s p%d %s M%d N%d K%d]' % ('K' if k.get('a_kmajor', True) else 'M', 'K' if k.get('b_kmajor', True) else 'M',
-                                                       k.get('precision', 3), 'acc' if k.get('accumulate') else ('dact' if k.get('dact') else 'st'),
-                                                       a[3], a[4], a[5])
-            _PROFILE_EVENTS.append((tag, e0, e1))
-            return r
-        return timed
-    for n in names:
-        g[n] = wrap(n, g[n])
-
-
-def profile_reset():
-    _PROFILE_EVENTS.clear()
-
-
-def profile_report(n_steps=1):
-    torch.cuda.synchronize()
-    agg = {}
-    for tag, e0, e1 in _PROFILE_EVENTS:
-        a = agg.setdefault(tag, [0, 0.0])
-        a[0] += 1; a[1] += e0.elapsed_time(e1) * 1e3
-    tot = sum(v[1] for v in agg.values())
-    rows = sorted(agg.items(), key=lambda kv: -kv[1][1])
-    return [{'op': k, 'calls_per_step': v[0] / n_steps, 'us_per_step': v[1] / n_steps, 'pct': 100 * v[1] / tot} for k, v in rows], tot / n_steps
-
-
-if _os.environ.get('NAR_PROFILE') == '1':
-    _install_profiler()

@@ -37,6 +37,9 @@ typedef struct nar_ctx nar_ctx;
 
 /* ---- context ------------------------------------------------------------------------- */
 int  nar_abi_version(void);
+/* sizeof of an ABI struct as this library was compiled: 0 nar_feature_plan, 1 nar_model_cfg, 2 nar_step_io,
+ * 3 nar_row_layout, 4 nar_gemm_epilogue, 5 nar_segment (bindings check their mirrors against it); -1 otherwise */
+int  nar_abi_struct_size(int which);
 const char* nar_status_string(int status);
 int  nar_ctx_create(int device, nar_ctx** out);
 int  nar_ctx_destroy(nar_ctx* ctx);
@@ -289,6 +292,81 @@ int nar_adam_tf(float* params, const float* grads, float* m, float* v, int64_t n
                 float* params_lo /* optional [n]: receives w - tf32_trunc(w) of the updated weights */, void* stream);
 /* lo[i] = x[i] - tf32_trunc(x[i])  (the second operand plane of the 3xTF32 GEMM)          */
 int nar_tf32_lo(const float* x, int64_t n, float* lo, void* stream);
+
+/* =====================================================================================================
+ * The whole step behind ONE call (replaces the single session.run(train_op) of nar_trainer_gcom.py:515-517 /
+ * MonitoredTrainingSession: sampler -> features -> CAR -> RNN -> FC -> scorer -> loss -> backward -> Adam,
+ * nar_model.py:102-728).  The engine sequences every kernel of the step from C: the caller stages the batch in
+ * HBM, fills a nar_step_io and makes one call per phase; no per-kernel host round trip is left.
+ *   nar_engine_prepare  the weight-independent front of a step (negatives, row lists, normalisation statistics,
+ *                       base rows): may run one step ahead on a side stream
+ *   nar_engine_step     forward (+ backward when io->train): gradients complete in cfg.grads on return-stream order
+ *   nar_engine_apply    TF-Adam over the flat parameter buffer (after the data-parallel gradient exchange, if any)
+ * Internally the step forks weight / bias gradients onto an engine-owned auxiliary stream (events, no host sync).
+ * ===================================================================================================== */
+#define NAR_MAX_LAYERS 4
+
+typedef struct {
+  /* dimensions */
+  int64_t num_items, C /*CAR_embedding_size*/, Hp /*rnn_units padded to 4*/, Fp /*feature row width*/, ctx_col0;
+  int32_t layers, rnn_cell /*0 = UGRNNCell (nar_model.py:1318)*/, ranking /*0 = MLP scorer (:444-500), 1 = cosine*/;
+  int32_t fwd_precision, bwd_precision;       /* nar_gemm_epilogue.precision of the forward / backward GEMMs */
+  int32_t dedup;                              /* 1: per-unique-id CAR layer 1 (csrc/car.cu); 0: every candidate row materialised */
+  int32_t use_aux_stream;                     /* 1: weight / bias gradients (and the forward session branch) on the auxiliary stream */
+  /* hyper-parameters */
+  int64_t K /*negatives per click*/, n_from_buffer, buf_len, n_norm;
+  float inv_temperature, reg_l2, lr, beta1, beta2, eps;
+  uint64_t sampler_seed;
+  int32_t world, rank;                        /* data parallel: rank 0 adds the regulariser term to the loss */
+  /* flat parameter buffers: params / params_lo / grads / adam_m / adam_v share offsets (floats) */
+  float *params, *params_lo, *grads, *adam_m, *adam_v;
+  int64_t n_params, reg_end;
+  int64_t off_W1, off_b1, off_W2, off_b2, off_W3, off_b3, off_W4, off_b4, off_gamma, off_beta;
+  int64_t off_M[4], off_c[4], ld_M[4];        /* matching_dense_layer_1..4 kernels / biases, leading dimensions */
+  int64_t off_Wx[NAR_MAX_LAYERS], off_Wh[NAR_MAX_LAYERS], off_rb[NAR_MAX_LAYERS];
+  /* feature plan: static part (segments, tables, metadata, created_at_ts, gamma / beta, column map) */
+  nar_feature_plan plan;
+} nar_model_cfg;
+
+typedef struct {
+  int64_t B /*local sessions*/, Bg /*global sessions*/, T, sess0 /*first local session*/, L /*local valid positions*/,
+          L_global /*sum(mask) over the global batch: the loss normaliser*/;
+  int64_t L_cap;                  /* positions the workspace was sized for (>= L) */
+  int64_t global_step;            /* optimiser steps applied so far; this step is number global_step + 1 */
+  uint32_t sampler_step;          /* counter of the negative sampler (training: global_step + 1) */
+  int32_t train;                  /* 1: forward + backward, 0: forward + loss only */
+  /* staged inputs (device) */
+  const int64_t *all_items /*[Bg,T+1] item_clicked | label_last_item*/, *event_ts /*[Bg,T]*/, *item_clicked /*[Bg,T]*/,
+                *label_next /*[Bg,T]*/, *buffer /*[buf_len]*/, *max_ts /*[1]*/;
+  const float* pop_norm;          /* [num_items] */
+  const int64_t* ctx_int[NAR_MAX_SRC];
+  const float* ctx_float[NAR_MAX_SRC];
+  const int32_t *pos_idx /*[L] flat b*T+t of the valid positions, session-major*/, *sess_off /*[B+1]*/;
+  /* buffers */
+  void* prep_ws;  int64_t prep_ws_bytes;      /* results of nar_engine_prepare (one slot per step in flight) */
+  void* ws;       int64_t ws_bytes;           /* activations / activation gradients of the step */
+  float* loss;                                /* [4] device: {cross-entropy (mean over L_global), l2 regulariser, -, -} */
+} nar_step_io;
+
+typedef struct nar_engine nar_engine;
+
+int nar_engine_create(nar_ctx* ctx, const nar_model_cfg* cfg /*host*/, nar_engine** out);
+int nar_engine_destroy(nar_engine* eng);
+/* cfg fields that may change between steps without re-creating the engine (lr, precisions, stream use, world / rank) */
+int nar_engine_update_cfg(nar_engine* eng, const nar_model_cfg* cfg /*host*/);
+/* bytes of nar_step_io.prep_ws / .ws for a global batch of Bg x T, B local sessions, room for L_cap valid positions */
+int nar_engine_workspace_bytes(const nar_engine* eng, int64_t Bg, int64_t B, int64_t T, int64_t L_cap, int32_t train,
+                               int64_t* prep_bytes /*host*/, int64_t* ws_bytes /*host*/);
+int nar_engine_prepare(nar_engine* eng, const nar_step_io* io /*host*/, void* stream);
+int nar_engine_step(nar_engine* eng, const nar_step_io* io /*host*/, void* stream);
+int nar_engine_apply(nar_engine* eng, const nar_step_io* io /*host*/, void* stream);
+/* device address / shape of a named intermediate of the LAST nar_engine_prepare / nar_engine_step with this io
+ * (parity tests, evaluation ranking): "neg", "neg_uidx", "row_pos", "row_item", "stats", "X", "H1", "E", "HO<i>", "F1",
+ * "PR", "logits", "base_pos", "base_item", ...  Returns NAR_ERR_INVALID for an unknown name.                       */
+int nar_engine_buffer(const nar_engine* eng, const nar_step_io* io /*host*/, const char* name, void** ptr /*host*/,
+                      int64_t* rows /*host*/, int64_t* ld /*host*/);
+/* kernels launched by this engine so far */
+int64_t nar_engine_launch_count(const nar_engine* eng);
 
 #ifdef __cplusplus
 }

@@ -75,6 +75,47 @@ def test_full_step_parity_tiny(case):
     _check_steps(res)
 
 
+@pytest.mark.parametrize('case', ['tinyB', 'tinyB_cold', 'g1'])
+def test_full_step_parity_every_candidate_row(case):
+    """dedup=False: every candidate row gathered and multiplied by W1 (the layout dropout will need) - same bars."""
+    import torch
+    from tools import gpu_step_check as g
+    if case == 'g1':
+        res = g.run_case('g1', 'B', 30, 2, hp_over=dict(batch_size=48), oracle_dtype=torch.float32, engine_kw=dict(dedup=False))
+    else:
+        res = g.run_case('tiny', 'B', 0 if case == 'tinyB_cold' else 5, 2, oracle_dtype=torch.float64, engine_kw=dict(dedup=False))
+    _check_steps(res)
+
+
+def test_dedup_matches_every_candidate_row():
+    """The per-unique-id CAR layer 1 is exact: same logits / loss as the path that materialises every candidate row, to
+    fp32 summation order (3xTF32 forward); gradients agree to the TF32 backward noise; run twice: bit-reproducible."""
+    import torch
+    from chameleon_recsys_b200.harness import make_problem, warm_state
+    from tools import gpu_step_check as g
+    pb = make_problem('g1', profile='B', batch_size=64)
+    warm_state(pb, 10)
+    f, l = pb.input_fn().get_next()
+    buf = pb.clicked_items_state.get_recent_clicks_buffer().copy()
+    pop = pb.clicked_items_state.get_articles_recent_pop_norm().astype(np.float32)
+    logical = pb.layout.init_logical(5)
+    res = {}
+    for dd in (False, True, True):
+        eng = g.make_engine(pb, dedup=dd)
+        eng.set_params(logical)
+        st = eng.stage(f, l, buf, pop)
+        eng.step(st, train=True, keep=True)
+        torch.cuda.synchronize()
+        res.setdefault(dd, []).append((eng.last['logits'].clone(), eng.loss_dev.clone(), eng.grads.clone(), eng.last['E'].clone()))
+    (lg0, ls0, g0, e0), (lg1, ls1, g1, e1), (lg2, ls2, g2, e2) = res[False][0], res[True][0], res[True][1]
+    assert float((e0 - e1).abs().max()) < 2e-5
+    assert float((lg0 - lg1).abs().max()) / float(lg0.abs().max()) < 2e-5
+    assert abs(float(ls0[0]) - float(ls1[0])) / float(ls0[0]) < 1e-5
+    scale = float(g0.abs().max())
+    assert float((g0 - g1).abs().max()) / scale < 2e-2
+    assert torch.equal(lg1, lg2) and torch.equal(e1, e2)            # forward: no atomics anywhere
+
+
 def test_full_step_parity_g1_shapes():
     """G1 dims (46K items, E=250, H=255, C=1024, K=50, F=477) at a batch the fp32 oracle finishes in seconds."""
     import torch

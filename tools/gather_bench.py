@@ -32,14 +32,14 @@ def main():
     eng = est._ensure_spec(None, None).model.engine
     f, l, buf, pop = batches[1]
     st = eng.stage(f, l, buf, pop, slot='gb')
-    eng.grads.zero_()
     eng.step(st, train=False, keep=True)
     L, K = st['L'], eng.K
     R = L + L * (K + 1)
     plan = eng.plan
-    planc = eng._plan_c(st)
+    planc = eng.feature_plan_c(st)
     t = st['t']
-    X = eng._buf('X', R, plan.Fp)
+    X = torch.empty(R, plan.Fp, device='cuda')
+    rows = ops.row_layout(R, L, K + 1, ctx_col0=plan.ctx_col0)
     dX = torch.randn(R, plan.Fp, device='cuda')
     row_pos, row_item = eng.last['row_pos'], eng.last['row_item']
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')
@@ -60,7 +60,7 @@ def main():
     Di = plan.item_emb_dim if plan.use_item_emb else 0
     gbytes = L * ((2 + K) * (E + Di) * 4 * 2 + (2 + K) * 8)
     moved = R * plan.Fp * 4 + R * (E + Di) * 4 + R * 12
-    med, mn = timeit(lambda: ops.gather_features(planc, row_pos, row_item, R, L, K + 1, t['event_ts'], t['max_ts'], X))
+    med, mn = timeit(lambda: ops.gather_features(planc, row_pos, row_item, rows, t['event_ts'], t['max_ts'], X))
     print(json.dumps({'kernel': 'gather_features', 'rows': R, 'Fp': plan.Fp, 'us_median': med * 1e3, 'us_min': mn * 1e3,
                       'algorithmic_GBps': gbytes / (med * 1e-3) / 1e9, 'moved_GBps': moved / (med * 1e-3) / 1e9,
                       'minb': os.environ.get('NAR_GATHER_MINB', 'default')}))
@@ -79,8 +79,8 @@ def main():
     med, mn = timeit(lambda: z.zero_())
     print(json.dumps({'kernel': 'empty launch', 'us_median': med * 1e3}))
     dg = torch.zeros(plan.Fp, device='cuda'); db = torch.zeros(plan.Fp, device='cuda')
-    planb = eng._plan_c(st)
-    med, mn = timeit(lambda: ops.gather_features_bwd(planb, row_pos, row_item, R, L, K + 1, t['event_ts'], t['max_ts'], dX, dg, db))
+    planb = eng.feature_plan_c(st)
+    med, mn = timeit(lambda: ops.gather_features_bwd(planb, row_pos, row_item, rows, t['event_ts'], t['max_ts'], dX, dg, db))
     print(json.dumps({'kernel': 'gather_features_bwd', 'rows': R, 'us_median': med * 1e3, 'us_min': mn * 1e3,
                       'read_GBps': R * plan.Fp * 4 / (med * 1e-3) / 1e9}))
 

@@ -51,12 +51,12 @@ def rel(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)) if a.size else 0.0
 
 
-def run_case(name, profile, warm, n_steps, hp_over=None, oracle_dtype=torch.float64, sync_state=True, **mk):
+def run_case(name, profile, warm, n_steps, hp_over=None, oracle_dtype=torch.float64, sync_state=True, engine_kw=None, **mk):
     pb = make_problem(name, profile=profile, **(hp_over or {}), **mk)
     hp = pb.hp
     if warm:
         warm_state(pb, warm)
-    eng = make_engine(pb)
+    eng = make_engine(pb, **(engine_kw or {}))
     orc = make_oracle(pb, oracle_dtype)
     logical = pb.layout.init_logical(hp.init_seed)
     eng.set_params(logical)
@@ -140,8 +140,7 @@ def run_case(name, profile, warm, n_steps, hp_over=None, oracle_dtype=torch.floa
         r['update_err_over_lr'] = max(upd) if upd else 0.0
         res['steps'].append(r)
         # host state update (hook.after_run)
-        items, ts = batch_clicks_for_state_update(feats['item_clicked'], feats['event_timestamp'], labels['label_last_item'])
-        pb.clicked_items_state.update_items_state(items, ts)
+        pb.clicked_items_state.update_from_batch(feats['item_clicked'], feats['event_timestamp'], labels['label_last_item'])
     return res
 
 

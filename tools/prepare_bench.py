@@ -27,7 +27,6 @@ def main():
         eng.world, eng.rank = world, 0          # shard like rank 0 of `world` (no collective is issued by prepare)
         f, l, buf, pop = batches[1]
         st = eng.stage(f, l, buf, pop, slot='pb')
-        ops.profile_enable(True) if hasattr(ops, 'profile_enable') else None
         ts = []
         for it in range(8):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

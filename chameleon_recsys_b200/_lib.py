@@ -50,6 +50,7 @@ class ModelCfg(C.Structure):
     _fields_ = [('num_items', C.c_int64), ('C', C.c_int64), ('Hp', C.c_int64), ('Fp', C.c_int64), ('ctx_col0', C.c_int64),
                 ('layers', C.c_int32), ('rnn_cell', C.c_int32), ('ranking', C.c_int32),
                 ('fwd_precision', C.c_int32), ('bwd_precision', C.c_int32), ('dedup', C.c_int32), ('use_aux_stream', C.c_int32),
+                ('keep_prob', C.c_float), ('novelty_reg_factor', C.c_float), ('dropout_seed', C.c_uint64),
                 ('K', C.c_int64), ('n_from_buffer', C.c_int64), ('buf_len', C.c_int64), ('n_norm', C.c_int64),
                 ('inv_temperature', C.c_float), ('reg_l2', C.c_float), ('lr', C.c_float), ('beta1', C.c_float),
                 ('beta2', C.c_float), ('eps', C.c_float),
@@ -74,6 +75,11 @@ class StepIO(C.Structure):
                 ('pos_idx', C.c_void_p), ('sess_off', C.c_void_p),
                 ('prep_ws', C.c_void_p), ('prep_ws_bytes', C.c_int64), ('ws', C.c_void_p), ('ws_bytes', C.c_int64),
                 ('loss', C.c_void_p)]
+
+
+class NoveltyReg(C.Structure):
+    _fields_ = [('factor', C.c_float), ('log_base', C.c_float), ('pop_norm', C.c_void_p), ('cand_ids', C.c_void_p),
+                ('loss_nov', C.c_void_p)]
 
 
 class GemmEpilogue(C.Structure):
@@ -120,8 +126,9 @@ _SIGNATURES = {
     'nar_sample_negatives': (C.c_int, [vp, vp, i64, i64, i64, i64, vp, i64, i64, i64, u64, u32, vp, vp, i64, vp]),
     'nar_mul_pred': (C.c_int, [vp, vp, i64, i64, i64, vp, vp]),
     'nar_mul_pred_bwd': (C.c_int, [vp, vp, vp, i64, i64, i64, C.c_int, vp, vp, vp]),
-    'nar_score_softmax_ce': (C.c_int, [vp, i64, i64, vp, i64, vp, i64, i64, f32, f32, vp, vp, vp, vp, vp, vp]),
-    'nar_cosine_softmax_ce': (C.c_int, [vp, vp, i64, i64, i64, f32, f32, vp, vp, vp, vp, vp]),
+    'nar_score_softmax_ce': (C.c_int, [vp, i64, i64, vp, i64, vp, i64, i64, f32, f32, vp, vp, vp, vp, vp, C.POINTER(NoveltyReg), vp]),
+    'nar_cosine_softmax_ce': (C.c_int, [vp, vp, i64, i64, i64, f32, f32, vp, vp, vp, vp, C.POINTER(NoveltyReg), vp]),
+    'nar_dropout_rows': (C.c_int, [vp, vp, i64, i64, i64, vp, i64, i64, i64, C.c_int, f32, u64, u32, vp]),
     'nar_rank_candidates': (C.c_int, [vp, vp, i64, i64, i32, vp, vp, vp, vp]),
     'nar_host_state_update': (C.c_int, [vp, i64, vp, vp, i64, i64, vp, vp, vp, vp, i64, C.c_double]),
     'nar_host_state_update_batch': (C.c_int, [vp, i64, vp, vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, i64, C.c_double]),

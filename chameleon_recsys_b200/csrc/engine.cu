@@ -48,7 +48,7 @@ struct PrepBufs {
 struct StepBufs {
   float *X, *dX, *H1, *E, *dE, *dH1, *F1, *PR, *logits, *PD, *dPD, *Z1, *Z2, *Z3, *dZ1, *dZ2, *dZ3, *dPR, *dF1, *dHO;
   float *GX[NAR_MAX_LAYERS], *HO[NAR_MAX_LAYERS], *GT[NAR_MAX_LAYERS], *CD[NAR_MAX_LAYERS], *dGX[NAR_MAX_LAYERS],
-        *HPV[NAR_MAX_LAYERS], *dHOb[NAR_MAX_LAYERS];
+        *HPV[NAR_MAX_LAYERS], *dHOb[NAR_MAX_LAYERS], *HOd[NAR_MAX_LAYERS];   // HOd: RNN outputs after DropoutWrapper
   float *PP, *PI, *PC, *DB;        // dedup: layer-1 pre-activations and their gradients
 };
 
@@ -117,6 +117,8 @@ int64_t step_carve(const nar_engine* e, int64_t L_cap, int train, void* base, St
     if (c.ranking == 0) {
       sb->dZ3 = cv.take<float>(Rc * 32); sb->dZ2 = cv.take<float>(Rc * 64); sb->dZ1 = cv.take<float>(Rc * 128); sb->dPD = cv.take<float>(Rc * C);
     }
+    if (c.keep_prob < 1.f)
+      for (int i = 0; i < c.layers; ++i) sb->HOd[i] = cv.take<float>(L_cap * Hp);
     if (c.dedup) {
       sb->dH1 = cv.take<float>(Rc * C);                    // candidate rows only; the input rows' dH1 is DB[0:L]
       sb->DB = cv.take<float>((3 * L_cap + U) * C);
@@ -198,7 +200,14 @@ int run_step(nar_engine* e, const nar_step_io* io, cudaStream_t main) {
   NAR_CHECK_CUDA(cudaMemsetAsync(io->loss, 0, 4 * sizeof(float), main));
   if (train) NAR_CHECK_CUDA(cudaMemsetAsync(c.grads, 0, (size_t)c.n_params * sizeof(float), main));
   if (L == 0) return NAR_OK;
+  // dropout (training steps only): masks are per candidate row, so every row must be materialised
+  const bool drop = train && c.keep_prob < 1.f;
+  if (drop && c.dedup) return NAR_ERR_INVALID;
+  const uint32_t dstep = (uint32_t)(io->global_step + 1);
   Seq s(e, io, main);
+  auto dropout = [&](const float* src, float* dst, int64_t rows, int64_t cols, const int32_t* rpos, int tid, cudaStream_t st) {
+    s.chk(nar_dropout_rows(src, dst, rows, cols, cols, rpos, L, n_cand, K, tid, c.keep_prob, c.dropout_seed, dstep, st));
+  };
   const float inv_count = 1.0f / (float)(io->L_global > 0 ? io->L_global : 1);
   const int64_t U = pb.U, NB = 2 * L + U;
 
@@ -213,6 +222,7 @@ int run_step(nar_engine* e, const nar_step_io* io, cudaStream_t main) {
   const int32_t* g_pos = c.dedup ? pb.base_pos : pb.row_pos;
   const int64_t* g_item = c.dedup ? pb.base_item : pb.row_item;
   s.chk(nar_gather_features(e->ctx, &plan, g_pos, g_item, &rl, io->event_ts, io->max_ts, sb.X, main));
+  if (drop) dropout(sb.X, sb.X, R, Fp, pb.row_pos, 0, main);          // nar_model.py:338-340, :351-353, :367-369
 
   // ---- session branch: RNN (nar_model.py:408, :1308-1342) + FC1 / FC2 (:410-438) on the L clicked rows
   auto session_branch = [&](cudaStream_t st) {
@@ -220,9 +230,12 @@ int run_step(nar_engine* e, const nar_step_io* io, cudaStream_t main) {
     for (int i = 0; i < c.layers; ++i) {
       s.fwd(rnn_in, i == 0 ? C : Hp, c.off_Wx[i], 2 * Hp, c.off_rb[i], sb.GX[i], 2 * Hp, L, 2 * Hp, n_in, NAR_ACT_NONE, st);
       s.chk(nar_ugrnn_fwd(e->ctx, sb.GX[i], s.W(c.off_Wh[i]), io->sess_off, B, Hp, sb.HO[i], sb.GT[i], sb.CD[i], st));
-      rnn_in = sb.HO[i]; n_in = Hp;
+      // DropoutWrapper(output_keep_prob) (nar_model.py:1330-1333): the cell's OUTPUT is dropped, its state is not
+      if (drop) dropout(sb.HO[i], sb.HOd[i], L, Hp, io->pos_idx, 8 + i, st);
+      rnn_in = drop ? sb.HOd[i] : sb.HO[i]; n_in = Hp;
     }
-    s.fwd(sb.HO[c.layers - 1], Hp, c.off_W3, 512, c.off_b3, sb.F1, 512, L, 512, Hp, NAR_ACT_LEAKY_RELU, st);
+    s.fwd(rnn_in, Hp, c.off_W3, 512, c.off_b3, sb.F1, 512, L, 512, Hp, NAR_ACT_LEAKY_RELU, st);
+    if (drop) dropout(sb.F1, sb.F1, L, 512, io->pos_idx, 4, st);                                  // nar_model.py:417-419
     s.fwd(sb.F1, 512, c.off_W4, C, c.off_b4, sb.PR, C, L, C, 512, NAR_ACT_TANH, st);
   };
 
@@ -242,7 +255,11 @@ int run_step(nar_engine* e, const nar_step_io* io, cudaStream_t main) {
   s.fwd(H1c, C, c.off_W2, C, c.off_b2, Ec, C, Rc, C, C, NAR_ACT_TANH, main);
   s.join();
 
-  // ---- scorer + loss (nar_model.py:444-517, :639-667)
+  // ---- scorer + loss (nar_model.py:444-517, :639-667), optional novelty regulariser (:673-683)
+  nar_novelty_reg nov; memset(&nov, 0, sizeof(nov));
+  nov.factor = c.novelty_reg_factor; nov.log_base = c.plan.log_base_novelty; nov.pop_norm = io->pop_norm;
+  nov.cand_ids = pb.row_item + L; nov.loss_nov = io->loss + 2;
+  const nar_novelty_reg* novp = c.novelty_reg_factor > 0.f ? &nov : nullptr;
   if (c.ranking == 0) {
     s.chk(nar_mul_pred(Ec, sb.PR, L, n_cand, C, sb.PD, main));
     s.fwd(sb.PD, C, c.off_M[0], c.ld_M[0], c.off_c[0], sb.Z1, 128, Rc, 128, C, NAR_ACT_LEAKY_RELU, main);
@@ -250,10 +267,10 @@ int run_step(nar_engine* e, const nar_step_io* io, cudaStream_t main) {
     s.fwd(sb.Z2, 64, c.off_M[2], c.ld_M[2], c.off_c[2], sb.Z3, 32, Rc, 32, 64, NAR_ACT_LEAKY_RELU, main);
     s.chk(nar_score_softmax_ce(sb.Z3, 32, 32, s.W(c.off_M[3]), c.ld_M[3], s.W(c.off_c[3]), L, n_cand, c.inv_temperature, inv_count,
                                sb.logits, io->loss, train ? sb.dZ3 : nullptr, train ? s.G(c.off_M[3]) : nullptr,
-                               train ? s.G(c.off_c[3]) : nullptr, main));
+                               train ? s.G(c.off_c[3]) : nullptr, novp, main));
   } else {
     s.chk(nar_cosine_softmax_ce(Ec, sb.PR, L, n_cand, C, c.inv_temperature, inv_count, sb.logits, io->loss,
-                                train ? sb.dE + L * C : nullptr, train ? sb.dPR : nullptr, main));
+                                train ? sb.dE + L * C : nullptr, train ? sb.dPR : nullptr, novp, main));
   }
   // every rank holds the same weights: the regulariser is added once (rank 0) so that a sum over ranks is exact
   if (c.reg_l2 > 0.f && c.rank == 0) s.chk(nar_l2_loss_add(c.params, c.reg_end, c.reg_l2, io->loss + 1, main));
@@ -277,13 +294,16 @@ int run_step(nar_engine* e, const nar_step_io* io, cudaStream_t main) {
   s.chk(nar_act_bwd(sb.dPR, sb.PR, L * C, NAR_ACT_TANH, sb.dPR, main));
   { cudaStream_t st = s.fork(); s.wgrad(sb.F1, 512, sb.dPR, C, c.off_W4, C, 512, C, L, st); s.bgrad(sb.dPR, C, L, C, c.off_b4, st); }
   s.dgrad(sb.dPR, C, c.off_W4, C, sb.dF1, 512, L, 512, C, NAR_ACT_LEAKY_RELU, sb.F1, 512, 0, main);
-  { cudaStream_t st = s.fork(); s.wgrad(sb.HO[c.layers - 1], Hp, sb.dF1, 512, c.off_W3, 512, Hp, 512, L, st); s.bgrad(sb.dF1, 512, L, 512, c.off_b3, st); }
+  if (drop) dropout(sb.dF1, sb.dF1, L, 512, io->pos_idx, 4, main);     // F1 holds the dropped activations: re-apply the mask to the gradient
+  const float* rnn_out = drop ? sb.HOd[c.layers - 1] : sb.HO[c.layers - 1];
+  { cudaStream_t st = s.fork(); s.wgrad(rnn_out, Hp, sb.dF1, 512, c.off_W3, 512, Hp, 512, L, st); s.bgrad(sb.dF1, 512, L, 512, c.off_b3, st); }
   s.dgrad(sb.dF1, 512, c.off_W3, 512, sb.dHO, Hp, L, Hp, 512, NAR_ACT_NONE, nullptr, 0, 0, main);
-  const float* dho = sb.dHO;
+  float* dho = sb.dHO;
   for (int i = c.layers - 1; i >= 0; --i) {
+    if (drop) dropout(dho, dho, L, Hp, io->pos_idx, 8 + i, main);       // gradient of the dropped cell output
     s.chk(nar_transpose_f32(s.W(c.off_Wh[i]), Hp, 2 * Hp, 2 * Hp, e->WhT[i], Hp, main));
     s.chk(nar_ugrnn_bwd(e->ctx, dho, sb.HO[i], sb.GT[i], sb.CD[i], e->WhT[i], io->sess_off, B, Hp, sb.dGX[i], sb.HPV[i], main));
-    const float* x_in = i == 0 ? sb.E : sb.HO[i - 1];
+    const float* x_in = i == 0 ? sb.E : (drop ? sb.HOd[i - 1] : sb.HO[i - 1]);
     const int64_t n_in = i == 0 ? C : Hp;
     {
       cudaStream_t st = s.fork();
@@ -318,6 +338,7 @@ int run_step(nar_engine* e, const nar_step_io* io, cudaStream_t main) {
     s.dgrad(sb.dE, C, c.off_W2, C, sb.dH1, C, R, C, C, NAR_ACT_LEAKY_RELU, sb.H1, C, 0, main);
     { cudaStream_t st = s.fork(); s.wgrad(sb.X, Fp, sb.dH1, C, c.off_W1, C, Fp, C, R, st); s.bgrad(sb.dH1, C, R, C, c.off_b1, st); }
     s.dgrad(sb.dH1, C, c.off_W1, C, sb.dX, Fp, R, Fp, C, NAR_ACT_NONE, nullptr, 0, 0, main);
+    if (drop) dropout(sb.dX, sb.dX, R, Fp, pb.row_pos, 0, main);
   }
   s.chk(nar_gather_features_bwd(e->ctx, &plan, g_pos, g_item, &rl, io->event_ts, io->max_ts, sb.dX, s.G(c.off_gamma),
                                 s.G(c.off_beta), main));

@@ -40,6 +40,27 @@ mul_pred_bwd_kernel(const float4* __restrict__ d_prod, const float4* __restrict_
   }
 }
 
+// Novelty regulariser (nar_model.py:517, :531-544, :673-683): total_loss -= factor * sum_l mask_l * sum_k q_lk * nov_lk
+// / sum(mask), q = softmax over the NEGATIVES only of the scaled scores, nov = -log_base(articles_recent_pop_norm[id]).
+// d/d(scaled score k) = -factor * inv_count * q_k * (nov_k - sum_j q_j nov_j); fused into the two softmax-CE kernels.
+struct NovArgs { float factor, inv_log_base; const float* pop_norm; const int64_t* cand_ids; float* loss_nov; };
+
+__device__ __forceinline__ float nov_of(const NovArgs& nv, int64_t l, int64_t n_cand, int64_t j) {
+  return -__fmul_rn(logf(nv.pop_norm[nv.cand_ids[l * n_cand + j]]), nv.inv_log_base);
+}
+// warp-cooperative: log-sum-exp of the negatives' scaled scores and their probability-weighted mean novelty
+__device__ __forceinline__ void nov_stats(const NovArgs& nv, const float* lg, int64_t l, int64_t n_cand, int lane, float& lse_n,
+                                          float& nbar) {
+  float mx = -INFINITY;
+  for (int64_t j = 1 + lane; j < n_cand; j += 32) mx = fmaxf(mx, lg[j]);
+  mx = warp_max(mx);
+  float se = 0.f, sn = 0.f;
+  for (int64_t j = 1 + lane; j < n_cand; j += 32) { const float e = expf(lg[j] - mx); se += e; sn = fmaf(e, nov_of(nv, l, n_cand, j), sn); }
+  se = warp_sum(se); sn = warp_sum(sn);
+  lse_n = mx + logf(se);
+  nbar = sn / se;
+}
+
 // one warp per position
 constexpr int CE_WARPS = 4;
 
@@ -47,7 +68,7 @@ __global__ void __launch_bounds__(CE_WARPS * 32)
 score_softmax_ce_kernel(const float* __restrict__ z3, int64_t ld_z, int width, const float* __restrict__ m4, int64_t ld_m4,
                         const float* __restrict__ c4, int64_t n_pos, int64_t n_cand, float inv_temp, float inv_count,
                         float* __restrict__ logits, float* __restrict__ loss_sum, float* __restrict__ d_z3,
-                        float* __restrict__ d_m4, float* __restrict__ d_c4) {
+                        float* __restrict__ d_m4, float* __restrict__ d_c4, const NovArgs nv) {
   const int lane = threadIdx.x & 31;
   const int64_t l = (int64_t)blockIdx.x * CE_WARPS + (threadIdx.x >> 5);
   if (l >= n_pos) return;
@@ -69,12 +90,20 @@ score_softmax_ce_kernel(const float* __restrict__ z3, int64_t ld_z, int width, c
   se = warp_sum(se);
   const float lse = mx + logf(se);
   if (lane == 0) atomicAdd(loss_sum, -(lg[0] - lse) * inv_count);
+  float lse_n = 0.f, nbar = 0.f;
+  const bool use_nov = nv.factor > 0.f && n_cand > 1;
+  if (use_nov) {
+    __syncwarp();
+    nov_stats(nv, lg, l, n_cand, lane, lse_n, nbar);
+    if (lane == 0) atomicAdd(nv.loss_nov, nv.factor * nbar * inv_count);
+  }
   if (d_z3 == nullptr) return;
   // gradient: d logit_j = (softmax_j - [j==0]) * inv_count ; ds_j = d logit_j * inv_temp
   float dc = 0.f;
   for (int64_t j = lane; j < n_cand; j += 32) {
     const float pj = expf(lg[j] - lse);
-    const float ds = (pj - (j == 0 ? 1.f : 0.f)) * inv_count * inv_temp;
+    float ds = (pj - (j == 0 ? 1.f : 0.f)) * inv_count * inv_temp;
+    if (use_nov && j > 0) ds -= nv.factor * inv_count * inv_temp * expf(lg[j] - lse_n) * (nov_of(nv, l, n_cand, j) - nbar);
     dc += ds;
     const float* z = z3 + (l * n_cand + j) * ld_z;
     float* dz = d_z3 + (l * n_cand + j) * ld_z;
@@ -92,7 +121,8 @@ score_softmax_ce_kernel(const float* __restrict__ z3, int64_t ld_z, int width, c
     if (k < width) {
       for (int64_t j = 0; j < n_cand; ++j) {
         const float pj = expf(lg[j] - lse);
-        const float ds = (pj - (j == 0 ? 1.f : 0.f)) * inv_count * inv_temp;
+        float ds = (pj - (j == 0 ? 1.f : 0.f)) * inv_count * inv_temp;
+        if (use_nov && j > 0) ds -= nv.factor * inv_count * inv_temp * expf(lg[j] - lse_n) * (nov_of(nv, l, n_cand, j) - nbar);
         acc = fmaf(ds, z3[(l * n_cand + j) * ld_z + k], acc);
       }
       atomicAdd(d_m4 + (int64_t)k * ld_m4, acc);
@@ -107,7 +137,7 @@ constexpr int COS_THREADS = 128;
 __global__ void __launch_bounds__(COS_THREADS)
 cosine_softmax_ce_kernel(const float* __restrict__ cand, const float* __restrict__ pred, int64_t n_cand, int C,
                          float inv_temp, float inv_count, float* __restrict__ logits, float* __restrict__ loss_sum,
-                         float* __restrict__ d_cand, float* __restrict__ d_pred) {
+                         float* __restrict__ d_cand, float* __restrict__ d_pred, const NovArgs nv) {
   extern __shared__ float sh[];
   float* sp = sh;                       // [C] pred row
   float* s_dot = sh + C;                // [n_cand] <cand_j, pred>
@@ -141,8 +171,18 @@ cosine_softmax_ce_kernel(const float* __restrict__ cand, const float* __restrict
     se = warp_sum(se);
     const float lse = mx + logf(se);
     if (lane == 0) atomicAdd(loss_sum, -(lg[0] - lse) * inv_count);
-    for (int64_t j = lane; j < n_cand; j += 32)
-      s_ds[j] = (expf(lg[j] - lse) - (j == 0 ? 1.f : 0.f)) * inv_count * inv_temp;
+    float lse_n = 0.f, nbar = 0.f;
+    const bool use_nov = nv.factor > 0.f && n_cand > 1;
+    if (use_nov) {
+      __syncwarp();
+      nov_stats(nv, lg, l, n_cand, lane, lse_n, nbar);
+      if (lane == 0) atomicAdd(nv.loss_nov, nv.factor * nbar * inv_count);
+    }
+    for (int64_t j = lane; j < n_cand; j += 32) {
+      float ds = (expf(lg[j] - lse) - (j == 0 ? 1.f : 0.f)) * inv_count * inv_temp;
+      if (use_nov && j > 0) ds -= nv.factor * inv_count * inv_temp * expf(lg[j] - lse_n) * (nov_of(nv, l, n_cand, j) - nbar);
+      s_ds[j] = ds;
+    }
   }
   __syncthreads();
   if (d_cand == nullptr) return;
@@ -227,26 +267,40 @@ extern "C" int nar_mul_pred_bwd(const float* d_prod, const float* cand, const fl
 
 extern "C" int nar_score_softmax_ce(const float* z3, int64_t ld_z, int64_t width, const float* m4, int64_t ld_m4, const float* c4,
                                     int64_t n_pos, int64_t n_cand, float inv_temperature, float inv_count, float* logits,
-                                    float* loss_sum, float* d_z3, float* d_m4, float* d_c4, void* stream) {
+                                    float* loss_sum, float* d_z3, float* d_m4, float* d_c4, const nar_novelty_reg* nov,
+                                    void* stream) {
   if (!z3 || !m4 || !c4 || !logits || !loss_sum) return NAR_ERR_INVALID;
+  nar::loss::NovArgs nv = {0.f, 0.f, nullptr, nullptr, nullptr};
+  if (nov && nov->factor > 0.f) {
+    if (!nov->pop_norm || !nov->cand_ids || !nov->loss_nov || !(nov->log_base > 1.f)) return NAR_ERR_INVALID;
+    nv.factor = nov->factor; nv.inv_log_base = 1.0f / logf(nov->log_base); nv.pop_norm = nov->pop_norm; nv.cand_ids = nov->cand_ids;
+    nv.loss_nov = nov->loss_nov;
+  }
   if (d_z3 && (!d_m4 || !d_c4)) return NAR_ERR_INVALID;
   if (n_pos <= 0) return NAR_OK;
   const unsigned grid = (unsigned)((n_pos + nar::loss::CE_WARPS - 1) / nar::loss::CE_WARPS);
   nar::loss::score_softmax_ce_kernel<<<grid, nar::loss::CE_WARPS * 32, 0, as_stream(stream)>>>(
-      z3, ld_z, (int)width, m4, ld_m4, c4, n_pos, n_cand, inv_temperature, inv_count, logits, loss_sum, d_z3, d_m4, d_c4);
+      z3, ld_z, (int)width, m4, ld_m4, c4, n_pos, n_cand, inv_temperature, inv_count, logits, loss_sum, d_z3, d_m4, d_c4, nv);
   NAR_LAUNCH_CHECK();
   return NAR_OK;
 }
 
 extern "C" int nar_cosine_softmax_ce(const float* cand, const float* pred, int64_t n_pos, int64_t n_cand, int64_t C, float inv_temperature,
-                                     float inv_count, float* logits, float* loss_sum, float* d_cand, float* d_pred, void* stream) {
+                                     float inv_count, float* logits, float* loss_sum, float* d_cand, float* d_pred,
+                                     const nar_novelty_reg* nov, void* stream) {
   if (!cand || !pred || !logits || !loss_sum) return NAR_ERR_INVALID;
+  nar::loss::NovArgs nv = {0.f, 0.f, nullptr, nullptr, nullptr};
+  if (nov && nov->factor > 0.f) {
+    if (!nov->pop_norm || !nov->cand_ids || !nov->loss_nov || !(nov->log_base > 1.f)) return NAR_ERR_INVALID;
+    nv.factor = nov->factor; nv.inv_log_base = 1.0f / logf(nov->log_base); nv.pop_norm = nov->pop_norm; nv.cand_ids = nov->cand_ids;
+    nv.loss_nov = nov->loss_nov;
+  }
   if (d_cand && !d_pred) return NAR_ERR_INVALID;
   if (n_pos <= 0) return NAR_OK;
   const size_t smem = (size_t)(C + 3 * n_cand) * sizeof(float);
   if (smem > 48 * 1024) return NAR_ERR_UNSUPPORTED;
   nar::loss::cosine_softmax_ce_kernel<<<(unsigned)n_pos, nar::loss::COS_THREADS, smem, as_stream(stream)>>>(
-      cand, pred, n_cand, (int)C, inv_temperature, inv_count, logits, loss_sum, d_cand, d_pred);
+      cand, pred, n_cand, (int)C, inv_temperature, inv_count, logits, loss_sum, d_cand, d_pred, nv);
   NAR_LAUNCH_CHECK();
   return NAR_OK;
 }

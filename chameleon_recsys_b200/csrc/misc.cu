@@ -91,6 +91,31 @@ transpose_kernel(const float* __restrict__ src, int64_t rows, int64_t cols, int6
   }
 }
 
+// dropout with counter-based masks (spec: oracle/dropout_ref.py): one Philox4x32-10 block per 4 consecutive columns
+__global__ void __launch_bounds__(256)
+dropout_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t rows, int cols4, int64_t ld,
+                    const int32_t* __restrict__ row_pos, int64_t n_input, int64_t n_cand, int64_t K, int tensor_id,
+                    float inv_keep, unsigned long long thr, uint32_t k0, uint32_t k1, uint32_t step) {
+  const int64_t total = rows * cols4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols4; const int cb = (int)(i - r * cols4);
+    unsigned long long key = (unsigned long long)(long long)row_pos[r];
+    int tid = tensor_id;
+    if (tensor_id == 0) {
+      if (r < n_input) tid = 1;
+      else { const int64_t j = (r - n_input) % n_cand; if (j == 0) tid = 2; else { tid = 3; key = key * (unsigned long long)K + (unsigned long long)(j - 1); } }
+    }
+    const Philox4 p = philox4x32_10((uint32_t)cb, (uint32_t)key, (uint32_t)((key >> 32) & 0xFFFFFFull) | ((uint32_t)tid << 24), step, k0, k1);
+    const float4 v = *reinterpret_cast<const float4*>(src + r * ld + 4 * cb);
+    float4 o;
+    o.x = (unsigned long long)p.x < thr ? v.x * inv_keep : 0.f;
+    o.y = (unsigned long long)p.y < thr ? v.y * inv_keep : 0.f;
+    o.z = (unsigned long long)p.z < thr ? v.z * inv_keep : 0.f;
+    o.w = (unsigned long long)p.w < thr ? v.w * inv_keep : 0.f;
+    *reinterpret_cast<float4*>(dst + r * ld + 4 * cb) = o;
+  }
+}
+
 static unsigned grid_for(int64_t n, int per_block) {
   int64_t g = (n + per_block - 1) / per_block;
   const int64_t cap = 148 * 8;
@@ -174,6 +199,21 @@ extern "C" int nar_adam_tf(float* params, const float* grads, float* m, float* v
       reinterpret_cast<float4*>(params), reinterpret_cast<const float4*>(grads), reinterpret_cast<float4*>(m),
       reinterpret_cast<float4*>(v), n / 4, reg_end / 4, reg_l2, (float)lr_t, beta1, beta2, eps,
       reinterpret_cast<float4*>(params_lo));
+  NAR_LAUNCH_CHECK();
+  return NAR_OK;
+}
+
+extern "C" int nar_dropout_rows(const float* src, float* dst, int64_t rows, int64_t cols, int64_t ld, const int32_t* row_pos,
+                                int64_t n_input, int64_t n_cand, int64_t K, int tensor_id, float keep_prob, uint64_t seed,
+                                uint32_t step, void* stream) {
+  if (!src || !dst || !row_pos || (cols & 3) || (ld & 3) || tensor_id < 0 || tensor_id > 255) return NAR_ERR_INVALID;
+  if (!(keep_prob > 0.f) || keep_prob > 1.f) return NAR_ERR_INVALID;
+  if (tensor_id == 0 && (n_cand <= 0 || K != n_cand - 1)) return NAR_ERR_INVALID;
+  if (rows <= 0 || cols <= 0) return NAR_OK;
+  const unsigned long long thr = (unsigned long long)floor((double)keep_prob * 4294967296.0);
+  nar::misc::dropout_rows_kernel<<<nar::misc::grid_for(rows * (cols / 4), 256), 256, 0, as_stream(stream)>>>(
+      src, dst, rows, (int)(cols / 4), ld, row_pos, n_input, n_cand, K, tensor_id, 1.0f / keep_prob, thr, (uint32_t)seed,
+      (uint32_t)(seed >> 32) ^ 0x5DEECE66u, step);
   NAR_LAUNCH_CHECK();
   return NAR_OK;
 }

@@ -37,7 +37,8 @@ class NarEngine:
                  elapsed_days_smooth_log_base: float = 1.3, popularity_smooth_log_base: float = 2.0,
                  ranking: str = 'mlp', rnn_cell: str = 'ugrnn', sampler_seed: int = 42, device: Optional[int] = None,
                  fwd_precision: int = 3, bwd_precision: int = 1, process_group=None, max_batch: int = 0,
-                 dedup: Optional[bool] = None):
+                 dedup: Optional[bool] = None, keep_prob: float = 1.0, novelty_reg_factor: float = 0.0,
+                 dropout_seed: Optional[int] = None):
         if not torch.cuda.is_available():
             raise NarError('NarEngine needs a CUDA (sm_100a) device; there is no CPU fallback')
         if rnn_cell != 'ugrnn':
@@ -64,6 +65,15 @@ class NarEngine:
         self.V = plan.num_items
         # per-unique-id CAR layer 1 (exact; csrc/car.cu).  NAR_DEDUP=0 materialises every candidate row instead.
         self.dedup = (os.environ.get('NAR_DEDUP', '1') == '1') if dedup is None else bool(dedup)
+        # dropout (nar_model.py:338-340, :417-419, :1330-1333): masks are drawn per candidate row, so the rows cannot be
+        # shared between candidates - training with keep_prob < 1 materialises every row
+        self.keep_prob = float(keep_prob)
+        if not (0.0 < self.keep_prob <= 1.0):
+            raise ValueError('keep_prob must be in (0, 1]')
+        if self.keep_prob < 1.0:
+            self.dedup = False
+        self.nov_factor = float(novelty_reg_factor)
+        self.dropout_seed = self.seed if dropout_seed is None else int(dropout_seed)
         d = self.dev
         # ---- resident tables
         acr = np.zeros((self.V, plan.acr_ld), dtype=np.float32)
@@ -79,7 +89,7 @@ class NarEngine:
         self.adam_v = torch.zeros(n, device=d)
         self.params_lo = torch.zeros(n, device=d)      # w - tf32_trunc(w): B_lo plane of the 3xTF32 forward GEMMs
         self.global_step = 0
-        self.loss_dev = torch.zeros(4, device=d)          # [xe_sum, reg, -, -]
+        self.loss_dev = torch.zeros(4, device=d)          # [xe, l2 regulariser, novelty regulariser, -]: total = [0] + [1] - [2]
         self.loss_host = torch.zeros(4).pin_memory()
         self._loss_hosts = [self.loss_host, torch.zeros(4).pin_memory()]    # two in flight: submit(n+1) before result(n)
         self._loss_slot = 0
@@ -119,7 +129,7 @@ class NarEngine:
     # ------------------------------------------------------------------ C-side configuration
     def _dynamic_key(self):
         return (self.use_aux_stream, self.world, self.rank, self.lr, self.fwd_prec, self.bwd_prec, self.dedup,
-                self.params.data_ptr(), self.params_lo.data_ptr(), self.K, self.n_from_buffer)
+                self.params.data_ptr(), self.params_lo.data_ptr(), self.K, self.n_from_buffer, self.keep_prob, self.nov_factor)
 
     def _make_cfg(self) -> ModelCfg:
         lay, pl = self.layout, self.plan
@@ -128,6 +138,8 @@ class NarEngine:
         c.layers, c.rnn_cell, c.ranking = self.layers, 0, 0 if self.ranking == 'mlp' else 1
         c.fwd_precision, c.bwd_precision = self.fwd_prec, self.bwd_prec
         c.dedup, c.use_aux_stream = int(self.dedup), int(self.use_aux_stream)
+        c.keep_prob, c.novelty_reg_factor = self.keep_prob, self.nov_factor
+        c.dropout_seed = self.dropout_seed & 0xFFFFFFFFFFFFFFFF
         c.K, c.n_from_buffer, c.buf_len, c.n_norm = self.K, self.n_from_buffer, self.buf_len, self.n_norm
         c.inv_temperature, c.reg_l2, c.lr = 1.0 / self.tau, self.reg, self.lr
         c.beta1, c.beta2, c.eps = 0.9, 0.999, 1e-8
@@ -524,8 +536,8 @@ class NarEngine:
     def result(self, out: dict) -> dict:
         out['done'].synchronize()
         host = out['loss_host']
-        out['xe_loss'] = float(host[0]); out['reg_loss'] = float(host[1])
-        out['total_loss'] = out['xe_loss'] + out['reg_loss']
+        out['xe_loss'] = float(host[0]); out['reg_loss'] = float(host[1]); out['nov_reg_loss'] = float(host[2])
+        out['total_loss'] = out['xe_loss'] + out['reg_loss'] - out['nov_reg_loss']
         return out
 
     # ---- evaluation (ModeKeys.EVAL): forward + ranking of the 1+K candidates + HR@n / MRR@n accumulators
@@ -564,8 +576,8 @@ class NarEngine:
             torch.distributed.all_reduce(self.loss_dev, group=self.pg)
         self.loss_host.copy_(self.loss_dev, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        out['xe_loss'] = float(self.loss_host[0]); out['reg_loss'] = float(self.loss_host[1])
-        out['total_loss'] = out['xe_loss'] + out['reg_loss']
+        out['xe_loss'] = float(self.loss_host[0]); out['reg_loss'] = float(self.loss_host[1]); out['nov_reg_loss'] = float(self.loss_host[2])
+        out['total_loss'] = out['xe_loss'] + out['reg_loss'] - out['nov_reg_loss']
         out['stage'] = st
         return out
 
@@ -580,6 +592,6 @@ class NarEngine:
         out['stage'] = st
         if sync:
             torch.cuda.current_stream().synchronize()
-            out['xe_loss'] = float(self.loss_host[0]); out['reg_loss'] = float(self.loss_host[1])
-            out['total_loss'] = out['xe_loss'] + out['reg_loss']
+            out['xe_loss'] = float(self.loss_host[0]); out['reg_loss'] = float(self.loss_host[1]); out['nov_reg_loss'] = float(self.loss_host[2])
+            out['total_loss'] = out['xe_loss'] + out['reg_loss'] - out['nov_reg_loss']
         return out

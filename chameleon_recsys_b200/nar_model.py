@@ -52,11 +52,6 @@ class NARModuleModel:
                  rnn_cell='ugrnn', ranking='mlp', sampler_seed=42, init_seed=42, device=None,
                  process_group=None, fwd_precision=3, bwd_precision=1):
         from .engine import NarEngine          # imports torch + the CUDA library; fails loudly without them
-        if keep_prob != 1.0 and mode == ModeKeys.TRAIN:
-            # every shipped script trains with dropout_keep_prob 1.0 (run_nar_train_gcom_local.sh:20)
-            raise NotImplementedError('dropout (keep_prob < 1) is not implemented on the B200 path')
-        if novelty_reg_factor > 0.0:
-            raise NotImplementedError('novelty_reg_factor > 0 (nar_model.py:673-683) is not implemented yet')
         self.mode = mode
         self.lr = lr
         self.keep_prob = keep_prob
@@ -87,7 +82,9 @@ class NARModuleModel:
                                 popularity_smooth_log_base=popularity_smooth_log_base, ranking=ranking,
                                 rnn_cell=rnn_cell, sampler_seed=sampler_seed, device=device,
                                 process_group=process_group, fwd_precision=fwd_precision,
-                                bwd_precision=bwd_precision)
+                                bwd_precision=bwd_precision,
+                                keep_prob=keep_prob if mode == ModeKeys.TRAIN else 1.0,
+                                novelty_reg_factor=novelty_reg_factor)
         self.engine.set_params(self.layout.init_logical(init_seed))
         # fetch targets of the reference hook (numpy after each run)
         self.item_clicked = None

@@ -182,19 +182,25 @@ def mul_pred_bwd(d_prod, cand, pred, n_pos, n_cand, Cdim, d_cand, d_pred, cand_a
           'nar_mul_pred_bwd')
 
 
-def score_softmax_ce(z3, ld_z, width, m4, ld_m4, c4, n_pos, n_cand, inv_temp, inv_count, logits, loss_sum, d_z3, d_m4, d_c4):
+def novelty_reg(factor, log_base, pop_norm, cand_ids, loss_nov) -> _lib.NoveltyReg:
+    return _lib.NoveltyReg(factor, log_base, pop_norm.data_ptr(), cand_ids.data_ptr(), loss_nov.data_ptr())
+
+
+def score_softmax_ce(z3, ld_z, width, m4, ld_m4, c4, n_pos, n_cand, inv_temp, inv_count, logits, loss_sum, d_z3, d_m4, d_c4, nov=None):
     global LAUNCHES
     LAUNCHES += 1
     check(_lib.load().nar_score_softmax_ce(_p(z3), ld_z, width, _p(m4), ld_m4, _p(c4), n_pos, n_cand, inv_temp, inv_count,
-                                           _p(logits), _p(loss_sum), _p(d_z3), _p(d_m4), _p(d_c4), _stream()),
+                                           _p(logits), _p(loss_sum), _p(d_z3), _p(d_m4), _p(d_c4),
+                                           C.byref(nov) if nov is not None else None, _stream()),
           'nar_score_softmax_ce')
 
 
-def cosine_softmax_ce(cand, pred, n_pos, n_cand, Cdim, inv_temp, inv_count, logits, loss_sum, d_cand, d_pred):
+def cosine_softmax_ce(cand, pred, n_pos, n_cand, Cdim, inv_temp, inv_count, logits, loss_sum, d_cand, d_pred, nov=None):
     global LAUNCHES
     LAUNCHES += 1
     check(_lib.load().nar_cosine_softmax_ce(_p(cand), _p(pred), n_pos, n_cand, Cdim, inv_temp, inv_count, _p(logits),
-                                            _p(loss_sum), _p(d_cand), _p(d_pred), _stream()), 'nar_cosine_softmax_ce')
+                                            _p(loss_sum), _p(d_cand), _p(d_pred), C.byref(nov) if nov is not None else None,
+                                            _stream()), 'nar_cosine_softmax_ce')
 
 
 def rank_candidates(logits, cand_ids, n_pos, n_cand, top_n, pred_ids, pred_probs, metrics):
@@ -202,6 +208,15 @@ def rank_candidates(logits, cand_ids, n_pos, n_cand, top_n, pred_ids, pred_probs
     LAUNCHES += 1
     check(_lib.load().nar_rank_candidates(_p(logits), _p(cand_ids), n_pos, n_cand, top_n, _p(pred_ids), _p(pred_probs),
                                           _p(metrics), _stream()), 'nar_rank_candidates')
+
+
+def dropout_rows(src, dst, rows, cols, ld, row_pos, n_input, n_cand, K, tensor_id, keep_prob, seed, step):
+    """dst = src * mask / keep_prob with the counter-based masks of oracle/dropout_ref.py (tensor_id 0: feature rows)."""
+    global LAUNCHES
+    LAUNCHES += 1
+    check(_lib.load().nar_dropout_rows(_p(src), _p(dst), rows, cols, ld, _p(row_pos), n_input, n_cand, K, tensor_id, keep_prob,
+                                       C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), C.c_uint32(step & 0xFFFFFFFF), _stream()),
+          'nar_dropout_rows')
 
 
 def colsum_add(x, rows, cols, ld, out):

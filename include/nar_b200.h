@@ -230,15 +230,26 @@ int nar_mul_pred_bwd(const float* d_prod, const float* cand, const float* pred, 
  * forward and backward in one pass.  z3 [n_pos*n_cand, ld_z] ; logits [n_pos,n_cand] ;
  * loss_sum += sum_l -(logp[l,0]) * inv_count ; d_z3 = d(loss)/d(z3) (before leaky');
  * d_m4[k] += ..., d_c4 += ...                                                              */
+/* optional novelty regulariser (nar_model.py:517, :531-544, :673-683): total_loss -= factor * mean over the valid
+ * positions of sum_k q_k * nov_k, q = softmax over the NEGATIVES only of the scaled scores, nov_k =
+ * -log_base(pop_norm[id_k]); its value is added to loss_nov[0] and its gradient to the negatives' score gradients */
+typedef struct {
+  float factor;               /* novelty_reg_factor; <= 0: off */
+  float log_base;             /* popularity_smooth_log_base */
+  const float* pop_norm;      /* [num_items] articles_recent_pop_norm */
+  const int64_t* cand_ids;    /* [n_pos*n_cand] candidate ids, positive first */
+  float* loss_nov;            /* [1] */
+} nar_novelty_reg;
+
 int nar_score_softmax_ce(const float* z3, int64_t ld_z, int64_t width, const float* m4, int64_t ld_m4,
                          const float* c4, int64_t n_pos, int64_t n_cand, float inv_temperature,
                          float inv_count, float* logits, float* loss_sum, float* d_z3,
-                         float* d_m4, float* d_c4, void* stream);
+                         float* d_m4, float* d_c4, const nar_novelty_reg* nov /*host, or NULL*/, void* stream);
 /* cosine mode (north_star wording; nar_model.py:437 commented l2-normalise): logits =
  * <l2n(pred), l2n(cand)>/temperature fused with the same softmax-CE; writes d_cand, d_pred. */
 int nar_cosine_softmax_ce(const float* cand, const float* pred, int64_t n_pos, int64_t n_cand, int64_t C,
                           float inv_temperature, float inv_count, float* logits, float* loss_sum,
-                          float* d_cand, float* d_pred, void* stream);
+                          float* d_cand, float* d_pred, const nar_novelty_reg* nov /*host, or NULL*/, void* stream);
 
 /* ---- evaluation ranking (ModeKeys.EVAL: rank_items_by_predicted_prob nar_model.py:777-795 = tf.nn.top_k over all
  *      1+K candidates, sparse_recall_at_top_k :835-840, define_mrr_metric :862-885).  logits [n_pos,n_cand] as written
@@ -273,6 +284,18 @@ int nar_state_update(const int64_t* old_items, const int64_t* old_ts, int64_t ca
                      const int64_t* event_ts, int64_t Bg, int64_t T, int64_t hours_ms, int64_t* new_items,
                      int64_t* new_ts, int64_t* recent_pop, float* pop_norm, double* pop_norm64, int64_t* articles_pop,
                      int64_t num_items, double min_norm_pop, int* err, void* stream);
+
+/* ---- dropout (replaces tf.layers.dropout nar_model.py:338-340 / :351-353 / :367-369 / :417-419 and
+ *      DropoutWrapper(output_keep_prob) :1330-1333).  dst[r,c] = src[r,c] * keep(r,c) / keep_prob; the masks come from
+ *      the counter-based generator specified in oracle/dropout_ref.py (Philox4x32-10 keyed by seed, counter = column
+ *      block, row key, tensor id, step) so that forward, backward and the oracle draw the same bits.
+ *      tensor_id > 0: every row belongs to that tensor, row key = row_pos[r] (flat position b*T+t).
+ *      tensor_id == 0: feature rows in the n_cand > 0 layout of nar_row_layout: rows [0,n_input) tensor 1 (key =
+ *      position), then per position the positive (tensor 2, key = position) and K negatives (tensor 3, key =
+ *      position*K + k).  In place (dst == src) is allowed.                                                        */
+int nar_dropout_rows(const float* src, float* dst, int64_t rows, int64_t cols, int64_t ld, const int32_t* row_pos,
+                     int64_t n_input, int64_t n_cand, int64_t K, int tensor_id, float keep_prob, uint64_t seed,
+                     uint32_t step, void* stream);
 
 /* ---- small helpers ------------------------------------------------------------------ */
 /* out[c] += sum_r x[r,c]   (bias gradients)                                                */
@@ -313,6 +336,9 @@ typedef struct {
   int32_t fwd_precision, bwd_precision;       /* nar_gemm_epilogue.precision of the forward / backward GEMMs */
   int32_t dedup;                              /* 1: per-unique-id CAR layer 1 (csrc/car.cu); 0: every candidate row materialised */
   int32_t use_aux_stream;                     /* 1: weight / bias gradients (and the forward session branch) on the auxiliary stream */
+  float keep_prob;                            /* dropout_keep_prob (training steps only; < 1 needs dedup == 0) */
+  float novelty_reg_factor;                   /* nar_model.py:673-683; 0 = off */
+  uint64_t dropout_seed;
   /* hyper-parameters */
   int64_t K /*negatives per click*/, n_from_buffer, buf_len, n_norm;
   float inv_temperature, reg_l2, lr, beta1, beta2, eps;

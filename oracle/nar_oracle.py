@@ -45,7 +45,8 @@ class NarOracle:
                  softmax_temperature=1.0, reg_weight_decay=0.0, recent_clicks_for_normalization=1000,
                  elapsed_days_smooth_log_base=1.3, popularity_smooth_log_base=2.0, CAR_embedding_size=256,
                  rnn_units=256, rnn_num_layers=1, max_cardinality_for_ohe=10, lr=1e-3,
-                 rnn_cell='ugrnn', ranking='mlp', dtype=torch.float32):
+                 rnn_cell='ugrnn', ranking='mlp', dtype=torch.float32, keep_prob=1.0, novelty_reg_factor=0.0,
+                 dropout_seed=42, int2log=None):
         self.scfg = session_features_config
         self.acfg = articles_features_config
         self.icfg = internal_features_config
@@ -65,6 +66,12 @@ class NarOracle:
         self.lr = float(lr)
         self.rnn_cell = rnn_cell
         self.ranking = ranking
+        self.keep_prob = float(keep_prob)
+        self.nov_factor = float(novelty_reg_factor)
+        self.dropout_seed = int(dropout_seed)
+        # internal (HBM) column -> logical column of the product's feature rows: the dropout spec is indexed by the former
+        self.int2log = None if int2log is None else np.asarray(int2log, dtype=np.int64)
+        self._drop = None          # (step,) while a training forward with dropout runs
         self.V = int(articles_features_config['article_id']['cardinality'])
         self.adam_m: Dict[str, torch.Tensor] = {}
         self.adam_v: Dict[str, torch.Tensor] = {}
@@ -175,6 +182,23 @@ class NarOracle:
             feats.append(self._normalize_values(nov, stats))
         return torch.cat(feats, dim=-1)
 
+    # ------------------------------------------------------------------ dropout (spec: oracle/dropout_ref.py)
+    def _dropout(self, x, tensor_id, row_key, feature_rows=False):
+        """tf.layers.dropout(rate = 1 - keep_prob, training=True) with the counter-based masks of dropout_ref."""
+        if self._drop is None or self.keep_prob >= 1.0:
+            return x
+        from . import dropout_ref
+        n_cols = x.shape[-1]
+        if feature_rows:
+            Fp = len(self.int2log)
+            mi = dropout_ref.keep_mask(self.dropout_seed, self._drop, tensor_id, row_key, Fp, self.keep_prob)
+            valid = self.int2log >= 0
+            m = np.zeros(mi.shape[:-1] + (n_cols,), dtype=bool)
+            m[..., self.int2log[valid]] = mi[..., valid]
+        else:
+            m = dropout_ref.keep_mask(self.dropout_seed, self._drop, tensor_id, row_key, n_cols, self.keep_prob)
+        return x * torch.as_tensor(m).to(self.dtype) / self.keep_prob
+
     # ------------------------------------------------------------------ layers
     def _dense(self, x, name, act):
         y = x @ self._p(name + '/kernel') + self._p(name + '/bias')
@@ -189,8 +213,10 @@ class NarOracle:
         return self._dense(self._dense(x, 'main/CAR/PreCAR_representation', 'leaky'),
                            'main/CAR/CAR_representation', 'tanh')
 
-    def rnn(self, x, lengths):
-        """nar_model.py:1308-1342: MultiRNNCell of UGRNNCell inside dynamic_rnn(sequence_length)."""
+    def rnn(self, x, lengths, pos_key=None):
+        """nar_model.py:1308-1342: MultiRNNCell of UGRNNCell inside dynamic_rnn(sequence_length); every cell wrapped in
+        DropoutWrapper(output_keep_prob) (:1330-1333): the OUTPUT of a cell is dropped (what the next layer / FC1
+        sees), the state it carries to the next time step is not."""
         B, T, _ = x.shape
         H = self.H
         states = [torch.zeros(B, H, dtype=self.dtype) for _ in range(self.layers)]
@@ -206,7 +232,7 @@ class NarOracle:
                 g = torch.sigmoid(g_act + 1.0)                     # forget_bias = 1.0
                 h = g * states[i] + (1.0 - g) * c
                 new_states.append(h)
-                inp = h
+                inp = h if pos_key is None else self._dropout(h, 8 + i, pos_key[:, t])
             alive = (t < lengths).to(self.dtype).unsqueeze(-1)
             outs.append(inp * alive)                                # zero output past the length
             states = [alive * ns + (1.0 - alive) * s for ns, s in zip(new_states, states)]
@@ -225,8 +251,12 @@ class NarOracle:
 
     # ------------------------------------------------------------------ forward
     def forward(self, features: Dict[str, np.ndarray], labels: Dict[str, np.ndarray], negatives: np.ndarray,
-                buffer: np.ndarray, pop_norm: np.ndarray, sum_mask_global: Optional[float] = None):
-        """-> dict with total_loss, xe_loss, reg_loss, logits [B,T,1+K] (already / temperature), mask, ..."""
+                buffer: np.ndarray, pop_norm: np.ndarray, sum_mask_global: Optional[float] = None,
+                train_step: Optional[int] = None, session0: int = 0):
+        """-> dict with total_loss, xe_loss, reg_loss, logits [B,T,1+K] (already / temperature), mask, ...
+        ``train_step`` (the optimiser step number, 1-based) switches dropout on (training mode, keep_prob < 1);
+        ``session0`` = global index of the first session (data-parallel shards draw the masks of their own rows)."""
+        self._drop = int(train_step) if (train_step is not None and self.keep_prob < 1.0) else None
         item_clicked = torch.as_tensor(features['item_clicked']).long()
         event_ts = torch.as_tensor(features['event_timestamp']).long().unsqueeze(-1)
         lengths = torch.as_tensor(features['session_size']).long() - 1          # :227
@@ -246,17 +276,23 @@ class NarOracle:
         gamma = self._p('main/user_items_contextual_features/input_features_center_scale/gamma_scale')
         beta = self._p('main/user_items_contextual_features/input_features_center_scale/beta_center')
 
+        pos_key = (np.arange(B, dtype=np.int64)[:, None] + session0) * T + np.arange(T, dtype=np.int64)[None, :]
+        Kn = neg.shape[2]
         f_in = self.item_features(item_clicked, event_ts, max_ts, buf, pop)                        # :328
         x_in = torch.cat([ctx, f_in], dim=2) * gamma + beta                                        # :332-333
+        x_in = self._dropout(x_in, 1, pos_key, feature_rows=True)                                  # :338-340
         f_pos = self.item_features(next_item, max_ts, max_ts, buf, pop)                            # :343
         x_pos = torch.cat([ctx, f_pos], dim=2) * gamma + beta
+        x_pos = self._dropout(x_pos, 2, pos_key, feature_rows=True)                                # :351-353
         f_neg = self.item_features(neg, max_ts, max_ts, buf, pop)                                  # :356
         ctx_t = ctx.unsqueeze(2).expand(B, T, neg.shape[2], ctx.shape[-1])
         x_neg = torch.cat([ctx_t, f_neg], dim=3) * gamma + beta                                    # :360-364
+        x_neg = self._dropout(x_neg, 3, pos_key[:, :, None] * Kn + np.arange(Kn, dtype=np.int64), feature_rows=True)   # :367-369
 
         e_in, e_pos, e_neg = self.CAR(x_in), self.CAR(x_pos), self.CAR(x_neg)                      # :382-403
-        r = self.rnn(e_in, lengths)                                                                # :408
+        r = self.rnn(e_in, lengths, pos_key if self._drop is not None else None)                   # :408
         fc1 = self._dense(r, 'main/session_representation/FC1', 'leaky')                           # :411
+        fc1 = self._dropout(fc1, 4, pos_key)                                                       # :417-419
         pred = self._dense(fc1, 'main/session_representation/FC2', 'tanh')                         # :423-438
         s_pos = self.scorer(e_pos, pred)                                                           # :478-485
         s_neg = self.scorer(e_neg, pred.unsqueeze(2)).squeeze(-1)                                  # :493-500
@@ -271,7 +307,15 @@ class NarOracle:
                 if self.regularised(name):
                     reg = reg + self.reg * (w ** 2).sum() / 2.0                                    # l2_regularizer
         total = xe + reg                                                                           # :667
-        return {'total_loss': total, 'xe_loss': xe, 'reg_loss': reg, 'logits': logits, 'mask': mask,
+        nov_reg = torch.zeros((), dtype=self.dtype)
+        if self.nov_factor > 0.0:
+            # nar_model.py:517 (softmax over the NEGATIVES only), :531-544 (raw novelty of the negatives), :673-683
+            neg_prob = torch.softmax(s_neg / self.tau, dim=-1)
+            nov = -self._log_base(pop[neg], self.pop_base)
+            nov_reg = self.nov_factor * ((neg_prob * nov).sum(-1) * m).sum() / denom
+            total = total - nov_reg
+        self._drop = None
+        return {'total_loss': total, 'xe_loss': xe, 'reg_loss': reg, 'nov_reg_loss': nov_reg, 'logits': logits, 'mask': mask,
                 'x_in': x_in, 'x_pos': x_pos, 'x_neg': x_neg, 'e_in': e_in, 'e_pos': e_pos, 'e_neg': e_neg,
                 'rnn_out': r, 'pred': pred, 'probs': torch.softmax(logits, dim=-1)}
 
@@ -314,7 +358,7 @@ class NarOracle:
                 p.sub_(lr_t * self.adam_m[n] / (self.adam_v[n].sqrt() + eps))
 
     def train_step(self, features, labels, negatives, buffer, pop_norm, sum_mask_global=None):
-        out = self.forward(features, labels, negatives, buffer, pop_norm, sum_mask_global)
+        out = self.forward(features, labels, negatives, buffer, pop_norm, sum_mask_global, train_step=self.step + 1)
         grads = self.compute_gradients(out)
         self.apply_gradients(grads)
         return out, grads

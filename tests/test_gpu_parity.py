@@ -48,6 +48,34 @@ def test_scorer_softmax_ce_mlp_and_cosine():
     assert not _fails(gpu_diag.fam_loss())
 
 
+def test_dropout_masks_match_spec():
+    """nar_dropout_rows draws exactly the bits oracle/dropout_ref.py specifies, for feature rows (tensor ids 1-3 by row
+    kind, negatives keyed by position*K + k) and for a fixed tensor id."""
+    import torch
+    from chameleon_recsys_b200 import ops
+    from oracle import dropout_ref
+    L, K, F = 7, 5, 24
+    n_cand = K + 1
+    R = L + L * n_cand
+    rs = np.random.RandomState(0)
+    pos = np.sort(rs.choice(2000, L, replace=False)).astype(np.int32) + (1 << 20)
+    row_pos = np.concatenate([pos, np.repeat(pos, n_cand)]).astype(np.int32)
+    x = torch.ones(R, F, device='cuda')
+    y = torch.empty_like(x)
+    ops.dropout_rows(x, y, R, F, F, torch.from_numpy(row_pos).cuda(), L, n_cand, K, 0, 0.75, 1234567890123, 9)
+    got = y.cpu().numpy()
+    want = np.zeros((R, F), dtype=bool)
+    want[:L] = dropout_ref.keep_mask(1234567890123, 9, 1, pos.astype(np.int64), F, 0.75)
+    cand = want[L:].reshape(L, n_cand, F)
+    cand[:, 0] = dropout_ref.keep_mask(1234567890123, 9, 2, pos.astype(np.int64), F, 0.75)
+    cand[:, 1:] = dropout_ref.keep_mask(1234567890123, 9, 3, pos.astype(np.int64)[:, None] * K + np.arange(K), F, 0.75)
+    assert np.array_equal(got != 0, want)
+    assert np.allclose(got[want], 1.0 / 0.75)
+    z = torch.empty(L, F, device='cuda')
+    ops.dropout_rows(x[:L], z, L, F, F, torch.from_numpy(pos).cuda(), 0, 0, 0, 9, 0.5, 42, 3)
+    assert np.array_equal(z.cpu().numpy() != 0, dropout_ref.keep_mask(42, 3, 9, pos.astype(np.int64), F, 0.5))
+
+
 def test_adam_colsum_l2():
     from tools import gpu_diag
     assert not _fails(gpu_diag.fam_misc())
@@ -65,12 +93,18 @@ def _check_steps(res, grad_tol=3e-2):
             assert s['update_err_over_lr'] < 0.2, s
 
 
-@pytest.mark.parametrize('case', ['tinyA', 'tinyB', 'tinyB_cold', 'tinyB_cos', 'tinyB_2l'])
+@pytest.mark.parametrize('case', ['tinyA', 'tinyB', 'tinyB_cold', 'tinyB_cos', 'tinyB_2l', 'tinyB_nov', 'tinyB_cos_nov', 'tinyB_drop',
+                                  'tinyB_2l_drop'])
 def test_full_step_parity_tiny(case):
     import torch
     from tools import gpu_step_check as g
     cfg = {'tinyA': ('A', 5, 3, None), 'tinyB': ('B', 5, 3, None), 'tinyB_cold': ('B', 0, 2, None),
-           'tinyB_cos': ('B', 5, 2, dict(ranking='cosine')), 'tinyB_2l': ('B', 5, 2, dict(rnn_num_layers=2))}[case]
+           'tinyB_cos': ('B', 5, 2, dict(ranking='cosine')), 'tinyB_2l': ('B', 5, 2, dict(rnn_num_layers=2)),
+           # novelty regulariser (nar_model.py:673-683) and dropout (:338-340, :417-419, :1330-1333)
+           'tinyB_nov': ('B', 5, 2, dict(novelty_reg_factor=0.5)),
+           'tinyB_cos_nov': ('B', 5, 2, dict(ranking='cosine', novelty_reg_factor=0.5)),
+           'tinyB_drop': ('B', 5, 2, dict(dropout_keep_prob=0.8)),
+           'tinyB_2l_drop': ('B', 5, 2, dict(rnn_num_layers=2, dropout_keep_prob=0.7))}[case]
     res = g.run_case('tiny', cfg[0], cfg[1], cfg[2], hp_over=cfg[3], oracle_dtype=torch.float64)
     _check_steps(res)
 

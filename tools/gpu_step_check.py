@@ -30,7 +30,8 @@ def make_oracle(pb, dtype=torch.float64):
                      popularity_smooth_log_base=hp.popularity_smooth_log_base,
                      CAR_embedding_size=hp.CAR_embedding_size, rnn_units=hp.rnn_units,
                      rnn_num_layers=hp.rnn_num_layers, max_cardinality_for_ohe=hp.max_cardinality_for_ohe,
-                     lr=hp.learning_rate, ranking=hp.ranking, dtype=dtype)
+                     lr=hp.learning_rate, ranking=hp.ranking, dtype=dtype, keep_prob=hp.dropout_keep_prob,
+                     novelty_reg_factor=hp.novelty_reg_factor, dropout_seed=hp.sampler_seed, int2log=pb.plan.int2log)
 
 
 def make_engine(pb, **kw):
@@ -43,7 +44,8 @@ def make_engine(pb, **kw):
                      recent_clicks_for_normalization=hp.recent_clicks_for_normalization,
                      elapsed_days_smooth_log_base=hp.elapsed_days_smooth_log_base,
                      popularity_smooth_log_base=hp.popularity_smooth_log_base, ranking=hp.ranking,
-                     sampler_seed=hp.sampler_seed, **kw)
+                     sampler_seed=hp.sampler_seed, keep_prob=hp.dropout_keep_prob, novelty_reg_factor=hp.novelty_reg_factor,
+                     **kw)
 
 
 def rel(a, b):

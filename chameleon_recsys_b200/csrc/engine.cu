@@ -463,6 +463,7 @@ extern "C" int nar_engine_buffer(const nar_engine* e, const nar_step_io* io, con
       {"logits", sb.logits, L, n_cand}, {"PD", sb.PD, Rc, c.C}, {"Z3", sb.Z3, Rc, 32}, {"PP", sb.PP, L, c.C},
       {"PI", sb.PI, pb.U, c.C}, {"PC", sb.PC, L, c.C}, {"DB", sb.DB, 3 * L + pb.U, c.C},
       {"HO0", sb.HO[0], L, c.Hp}, {"HO1", sb.HO[1], L, c.Hp}, {"HO2", sb.HO[2], L, c.Hp}, {"HO3", sb.HO[3], L, c.Hp},
+      {"HOd0", sb.HOd[0], L, c.Hp}, {"HOd1", sb.HOd[1], L, c.Hp}, {"HOd2", sb.HOd[2], L, c.Hp}, {"HOd3", sb.HOd[3], L, c.Hp},
       {"GX0", sb.GX[0], L, 2 * c.Hp}, {"dGX0", sb.dGX[0], L, 2 * c.Hp}};
   for (const Ent& t : tab)
     if (strcmp(t.n, name) == 0) {

@@ -456,14 +456,14 @@ class NarEngine:
         neg = self.buffer(st, 'neg').view(-1)[st['s0'] * T * K:(st['s0'] + B) * T * K].view(B, T, K)
         out = {'negatives': neg, 'L': L, 'loss': self.loss_dev, 'logits': self.buffer(st, 'logits') if L > 0 else None}
         if keep and L > 0:
-            self.last = self._collect(st)
+            self.last = self._collect(st, train)
         if prep.get('slot'):                                  # ran-ahead results: mark when this step is done with them
             ev = torch.cuda.Event()
             ev.record()
             self._slot_events[prep['slot']] = ev
         return out
 
-    def _collect(self, st: dict) -> Dict[str, torch.Tensor]:
+    def _collect(self, st: dict, train: bool = True) -> Dict[str, torch.Tensor]:
         """Intermediates for the parity tests.  In dedup mode the full [R, Fp] feature matrix the reference builds is
         reassembled from the base rows (clicked / positive rows, unique-negative item halves + the position's context)."""
         L, K, T = st['L'], self.K, st['T']
@@ -477,7 +477,9 @@ class NarEngine:
             xin, xpos, xu = X[:L], X[L:2 * L], X[2 * L:]
             xneg = torch.cat([xu[uidx][..., :c0], xin[:, None, c0:].expand(L, K, X.shape[1] - c0)], dim=2)
             X = torch.cat([xin, torch.cat([xpos[:, None, :], xneg], dim=1).reshape(L * n_cand, -1)], dim=0)
-        return dict(X=X.clone(), H1=b('H1'), E=b('E'), HO=[b('HO%d' % i) for i in range(self.layers)], F1=b('F1'), PR=b('PR'),
+        # with dropout the RNN OUTPUT the reference exposes is the dropped one (DropoutWrapper); the state is HO<i>
+        ho = 'HOd%d' if (self.keep_prob < 1.0 and train) else 'HO%d'
+        return dict(X=X.clone(), H1=b('H1'), E=b('E'), HO=[b(ho % i) for i in range(self.layers)], F1=b('F1'), PR=b('PR'),
                     logits=b('logits'), row_pos=b('row_pos').view(-1), row_item=b('row_item').view(-1),
                     stats=b('stats').view(-1).clone(),
                     neg=b('neg').view(-1)[st['s0'] * T * K:(st['s0'] + st['B']) * T * K].view(st['B'], T, K))

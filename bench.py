@@ -401,7 +401,7 @@ def run_ours(args):
     e2e_int = med['interactions']
     e2e_ms = med['ms']
     e2e_value = e2e_int / (e2e_ms * 1e-3)
-    h2d_bytes = int(np.mean([s['h2d_bytes'] for s in staged]))
+    h2d_bytes = int(est.h2d_bytes_per_step)          # the copy Estimator.train issues per step (device-resident state: no buffer / popularity upload)
 
     if rank != 0:
         if world > 1:

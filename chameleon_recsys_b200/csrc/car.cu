@@ -80,14 +80,33 @@ car_segsum_kernel(const float* __restrict__ dH1c, int64_t L, int K, int C, int64
     }
     return;
   }
-  // ---- unique entry u: rows (l, k) that drew it, positions ascending
-  __shared__ int s_l[NT], s_k[NT], s_n[NT], s_warp[NT / 32], s_cnt;
+  // ---- unique entry u: rows (l, k) that drew it, positions ascending.  The rows of a chunk of 256 positions are
+  // compacted into a list (ballot + warp prefix: order kept), then summed 8 at a time: 8 independent 128-bit loads in
+  // flight per thread, added in list order (a popular article is drawn by hundreds of positions - one dependent load
+  // after the other made this kernel 4x slower than the GEMM it follows).
+  __shared__ int s_row[NT * 2], s_warp[NT / 32], s_cnt, s_k0[NT], s_nn[NT];
   const int64_t u = (int64_t)blockIdx.x - L;
   const bool pad_slot = (u == U - 1);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float4 acc[4];                                     // C <= 4 * NT * 4 columns (host checks)
 #pragma unroll
   for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto add_rows = [&](int cnt) {
+    for (int e0 = 0; e0 < cnt; e0 += 8) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = (i * NT + threadIdx.x) * 4;
+        if (c < C) {
+          float4 v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            v[q] = e0 + q < cnt ? ld4(dH1c + (int64_t)s_row[e0 + q] * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) add4(acc[i], v[q]);
+        }
+      }
+    }
+  };
   for (int64_t l0 = 0; l0 < L; l0 += NT) {
     const int64_t l = l0 + threadIdx.x;
     int k0 = 0, n = 0;
@@ -103,27 +122,34 @@ car_segsum_kernel(const float* __restrict__ dH1c, int64_t L, int K, int C, int64
         k0 = kk; n = K - kk;
       }
     }
-    // ordered compaction of the chunk (ballot + warp prefix)
-    const unsigned b = __ballot_sync(0xffffffffu, n > 0);
-    if (lane == 0) s_warp[w] = __popc(b);
-    __syncthreads();
-    int base = 0;
-    for (int i = 0; i < w; ++i) base += s_warp[i];
-    if (n > 0) { const int o = base + __popc(b & ((1u << lane) - 1u)); s_l[o] = (int)(l - l0); s_k[o] = k0; s_n[o] = n; }
-    if (threadIdx.x == 0) { int t = 0; for (int i = 0; i < NT / 32; ++i) t += s_warp[i]; s_cnt = t; }
-    __syncthreads();
-    const int cnt = s_cnt;
-    for (int e = 0; e < cnt; ++e) {
-      const float* row = dH1c + ((l0 + s_l[e]) * n_cand + 1 + s_k[e]) * (int64_t)C;
-      for (int q = 0; q < s_n[e]; ++q) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int c = (i * NT + threadIdx.x) * 4;
-          if (c < C) add4(acc[i], ld4(row + (int64_t)q * C + c));
+    if (!pad_slot) {
+      // ordered compaction of the chunk
+      const unsigned b = __ballot_sync(0xffffffffu, n > 0);
+      if (lane == 0) s_warp[w] = __popc(b);
+      __syncthreads();
+      int base = 0;
+      for (int i = 0; i < w; ++i) base += s_warp[i];
+      if (n > 0) s_row[base + __popc(b & ((1u << lane) - 1u))] = (int)(l * n_cand + 1 + k0);
+      if (threadIdx.x == 0) { int t = 0; for (int i = 0; i < NT / 32; ++i) t += s_warp[i]; s_cnt = t; }
+      __syncthreads();
+      add_rows(s_cnt);
+      __syncthreads();
+    } else {
+      // rare (the pool ran out of candidates): position after position, its trailing padding rows in k order
+      s_k0[threadIdx.x] = k0; s_nn[threadIdx.x] = n;
+      __syncthreads();
+      for (int t = 0; t < NT; ++t) {
+        const int nn = s_nn[t], kk = s_k0[t];              // block-uniform
+        for (int p0 = 0; p0 < nn; p0 += 2 * NT) {
+          const int m = min(2 * NT, nn - p0);
+          __syncthreads();
+          for (int q = threadIdx.x; q < m; q += NT) s_row[q] = (int)((l0 + t) * n_cand + 1 + kk + p0 + q);
+          __syncthreads();
+          add_rows(m);
         }
       }
+      __syncthreads();
     }
-    __syncthreads();
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {

@@ -273,8 +273,9 @@ int run_step(nar_engine* e, const nar_step_io* io, cudaStream_t main) {
                                 train ? sb.dE + L * C : nullptr, train ? sb.dPR : nullptr, novp, main));
   }
   // every rank holds the same weights: the regulariser is added once (rank 0) so that a sum over ranks is exact
-  if (c.reg_l2 > 0.f && c.rank == 0) s.chk(nar_l2_loss_add(c.params, c.reg_end, c.reg_l2, io->loss + 1, main));
-  if (!train || s.rc) return s.rc;
+  // (off the critical path: it only feeds the reported loss)
+  if (c.reg_l2 > 0.f && c.rank == 0) { cudaStream_t st = s.fork(); s.chk(nar_l2_loss_add(c.params, c.reg_end, c.reg_l2, io->loss + 1, st)); }
+  if (!train || s.rc) { s.join(); return s.rc; }
 
   // =============================================================================================== backward
   float* dEc = sb.dE + L * C;

@@ -304,13 +304,13 @@ constexpr int BWD_THREADS = 256;
 __global__ void __launch_bounds__(BWD_THREADS)
 gather_features_bwd_kernel(const __grid_constant__ nar_feature_plan P, const int32_t* __restrict__ row_pos,
                            const int64_t* __restrict__ row_item, int64_t n_rows, int64_t n_input, int64_t n_cand,
-                           int64_t n_positive, int64_t n_full, int ctx_col0,
+                           int64_t n_positive, int64_t n_full, int ctx_col0, int rpb /* rows per CTA, <= BWD_ROWS */,
                            const int64_t* __restrict__ event_ts, const int64_t* __restrict__ max_ts,
                            const float* __restrict__ d_out, float* __restrict__ d_gamma, float* __restrict__ d_beta) {
   __shared__ int64_t s_pos[BWD_ROWS], s_item[BWD_ROWS], s_ts[BWD_ROWS];
   __shared__ int s_grp[BWD_ROWS];
-  const int64_t r0 = (int64_t)blockIdx.x * BWD_ROWS;
-  const int nr = (int)min((int64_t)BWD_ROWS, n_rows - r0);
+  const int64_t r0 = (int64_t)blockIdx.x * rpb;
+  const int nr = (int)min((int64_t)rpb, n_rows - r0);
   if (threadIdx.x < nr) {
     const int64_t r = r0 + threadIdx.x;
     const int64_t pos = row_pos[r];
@@ -325,7 +325,7 @@ gather_features_bwd_kernel(const __grid_constant__ nar_feature_plan P, const int
   for (int c = threadIdx.x; c < P.row_ld; c += BWD_THREADS) {
     const int si = P.col_seg[c];
     if (si == 255) continue;
-    const int nr = c >= ctx_col0 ? nr_ctx : (int)min((int64_t)BWD_ROWS, n_rows - r0);
+    const int nr = c >= ctx_col0 ? nr_ctx : (int)min((int64_t)rpb, n_rows - r0);
     const nar_segment& sg = P.seg[si];
     const int j = c - sg.col;
     const float gam = P.gamma[c];
@@ -708,9 +708,13 @@ extern "C" int nar_gather_features_bwd(nar_ctx* ctx, const nar_feature_plan* pla
   const int64_t n_rows = rows->n_rows, n_input = rows->n_input, n_cand = rows->n_cand;
   if (n_rows <= 0) return NAR_OK;
   const int64_t n_full = rows->n_full < n_rows ? (rows->n_full < 0 ? 0 : rows->n_full) : n_rows;
-  const unsigned grid = (unsigned)((n_rows + nar::feat::BWD_ROWS - 1) / nar::feat::BWD_ROWS);
+  // rows per CTA: 32 for long row lists; fewer when that would leave most SMs idle (the per-unique-id base rows of a
+  // step are ~2 K rows: 32 rows per CTA = 61 CTAs measured 65 us, latency bound)
+  int rpb = (int)(n_rows / (4 * (int64_t)ctx->sm_count));
+  rpb = rpb < 4 ? 4 : (rpb > nar::feat::BWD_ROWS ? nar::feat::BWD_ROWS : rpb);
+  const unsigned grid = (unsigned)((n_rows + rpb - 1) / rpb);
   nar::feat::gather_features_bwd_kernel<<<grid, nar::feat::BWD_THREADS, 0, as_stream(stream)>>>(
-      *plan, row_pos, row_item, n_rows, n_input, n_cand, rows->n_positive, n_full, (int)rows->ctx_col0, event_timestamp, max_ts,
+      *plan, row_pos, row_item, n_rows, n_input, n_cand, rows->n_positive, n_full, (int)rows->ctx_col0, rpb, event_timestamp, max_ts,
       d_out, d_gamma, d_beta);
   NAR_LAUNCH_CHECK();
   return NAR_OK;

@@ -633,7 +633,9 @@ extern "C" int nar_gemm_tf32(nar_ctx* ctx, int64_t M, int64_t N, int64_t K, cons
   const bool amn = !a_kmajor, bmn = !b_kmajor;
   static int occ_env = -1;
   if (occ_env < 0) { const char* e = getenv("NAR_GEMM_OCC2"); occ_env = e ? atoi(e) : 1; }
-  const bool occ2 = occ_env != 0 && !cluster;
+  // two CTAs per SM (half-depth rings) pay off when there are CTAs to pair up; a grid smaller than the GPU is latency
+  // bound on its serial k-loop instead: deep rings (one CTA per SM, 4-6 stages of TMA prefetch) serve it better
+  const bool occ2 = occ_env != 0 && !cluster && (n_tiles * m_tiles_launch * split >= (int64_t)ctx->sm_count || occ_env == 2);
 #define NAR_GEMM_CASE(a, b) \
   if (amn == a && bmn == b) { \
     if (mode == 0 && TM == 1 && TN == 2) return launch<a, b, 0, 1, 2, 2>(ta, tb, tbl, p, grid, st); \

@@ -84,12 +84,14 @@ class NarEngine:
         # ---- parameters (flat fp32 buffers; same offsets for grads / Adam slots)
         n = layout.total
         self.params = torch.zeros(n, device=d)
-        self.grads = torch.zeros(n, device=d)
+        # gradients and the 4 loss accumulators share ONE buffer, so that data parallel needs a single collective per step
+        self._grads_ext = torch.zeros(n + 4, device=d)
+        self.grads = self._grads_ext[:n]
         self.adam_m = torch.zeros(n, device=d)
         self.adam_v = torch.zeros(n, device=d)
         self.params_lo = torch.zeros(n, device=d)      # w - tf32_trunc(w): B_lo plane of the 3xTF32 forward GEMMs
         self.global_step = 0
-        self.loss_dev = torch.zeros(4, device=d)          # [xe, l2 regulariser, novelty regulariser, -]: total = [0] + [1] - [2]
+        self.loss_dev = self._grads_ext[n:]               # [xe, l2 regulariser, novelty regulariser, -]: total = [0] + [1] - [2]
         self.loss_host = torch.zeros(4).pin_memory()
         self._loss_hosts = [self.loss_host, torch.zeros(4).pin_memory()]    # two in flight: submit(n+1) before result(n)
         self._loss_slot = 0
@@ -112,6 +114,7 @@ class NarEngine:
         self._ws: Optional[torch.Tensor] = None
         self._prep_ws: Dict[str, torch.Tensor] = {}
         self._old = []                                # superseded workspaces, kept until the steps using them are done
+        self.dstate = None                            # DeviceClickedItemsState when the recent-clicks state lives in HBM
         self._handle = C.c_void_p()
         self._cfg = self._make_cfg()
         check(self._lib.nar_engine_create(self._ctx.handle, C.byref(self._cfg), C.byref(self._handle)), 'nar_engine_create')
@@ -260,16 +263,46 @@ class NarEngine:
             self._prep_ws[slot] = p
         return cap, p, self._ws
 
+    # ------------------------------------------------------------------ device-resident ClickedItemsState
+    def attach_device_state(self, host_state):
+        """Move the recent-clicks buffer / recent popularity into HBM (device_state.py, csrc/state.cu): from now on
+        ``stage(..., buffer=None, pop_norm=None)`` uploads neither (0.34 MB per G1 step) and ``advance_device_state``
+        folds a staged batch in on the device - no host pass, no per-step upload.  ``detach_device_state`` writes the
+        state back into the host object (checkpoints, evaluation hooks)."""
+        from .device_state import DeviceClickedItemsState
+        self.dstate = DeviceClickedItemsState(host_state, device=self.dev.index)
+        self._dstate_host = host_state
+        return self.dstate
+
+    def detach_device_state(self):
+        if self.dstate is not None:
+            self.dstate.to_host(self._dstate_host)
+            self.dstate = None
+
+    def advance_device_state(self, st: dict, stream: Optional[torch.cuda.Stream] = None):
+        """ItemsStateUpdaterHook.after_run on the device: fold the clicks of the batch staged in ``st`` into the state
+        (depends on the batch's ids / timestamps only, so it may run on the side stream right behind the batch's copy)."""
+        if self.dstate is None:
+            raise NarError('no device state attached')
+        t = st['t']
+        self.dstate.update(t['all_items'], t['event_ts'], has_clicks=st['has_clicks'], stream=stream)
+
     # ------------------------------------------------------------------ staging (host -> HBM, one copy)
-    def stage(self, features: Dict[str, np.ndarray], labels: Dict[str, np.ndarray], buffer: np.ndarray,
-              pop_norm: np.ndarray, slot: str = 'stage', stream: Optional[torch.cuda.Stream] = None) -> dict:
+    def stage(self, features: Dict[str, np.ndarray], labels: Dict[str, np.ndarray], buffer: Optional[np.ndarray],
+              pop_norm: Optional[np.ndarray], slot: str = 'stage', stream: Optional[torch.cuda.Stream] = None) -> dict:
         """Pack the step inputs into one pinned buffer and issue one async H2D copy.
-        ``features``/``labels`` hold the GLOBAL batch (all data-parallel ranks see the same arrays)."""
+        ``features``/``labels`` hold the GLOBAL batch (all data-parallel ranks see the same arrays).  ``buffer`` /
+        ``pop_norm`` None: the device-resident state is read instead (attach_device_state)."""
         item_clicked = np.ascontiguousarray(features['item_clicked'], dtype=np.int64)
         Bg, T = item_clicked.shape
-        buffer = np.asarray(buffer)
-        if buffer.size != self.buf_len:
-            raise ValueError('recent-clicks buffer has %d entries, engine was built for %d' % (buffer.size, self.buf_len))
+        use_dstate = buffer is None
+        if use_dstate:
+            if self.dstate is None:
+                raise NarError('stage(buffer=None) needs attach_device_state()')
+        else:
+            buffer = np.asarray(buffer)
+            if buffer.size != self.buf_len:
+                raise ValueError('recent-clicks buffer has %d entries, engine was built for %d' % (buffer.size, self.buf_len))
         # this rank's sessions + compact valid positions (session-major; flat index into the GLOBAL [Bg*T] arrays)
         sh = shard_sessions(np.asarray(features['session_size']), T, self.world, self.rank)
         s0, per, lens, L, L_global = sh['s0'], sh['per'], sh['lens'], sh['L'], sh['L_global']
@@ -279,11 +312,13 @@ class NarEngine:
         parts = [('all_items', all_items, np.int64), ('event_ts', ev, np.int64),
                  ('item_clicked', item_clicked, np.int64),
                  ('label_next', np.ascontiguousarray(labels['label_next_item'], dtype=np.int64), np.int64),
-                 ('buffer', np.ascontiguousarray(buffer, dtype=np.int64), np.int64),
                  ('max_ts', np.asarray([ev.max() if ev.size else 0], dtype=np.int64), np.int64)]
+        if not use_dstate:
+            parts.append(('buffer', np.ascontiguousarray(buffer, dtype=np.int64), np.int64))
         for name in self.plan.ctx_int_names:
             parts.append(('ci/' + name, np.ascontiguousarray(features[name], dtype=np.int64), np.int64))
-        parts.append(('pop_norm', np.ascontiguousarray(pop_norm, dtype=np.float32), np.float32))
+        if not use_dstate:
+            parts.append(('pop_norm', np.ascontiguousarray(pop_norm, dtype=np.float32), np.float32))
         for name in self.plan.ctx_float_names:
             parts.append(('cf/' + name, np.ascontiguousarray(features[name], dtype=np.float32), np.float32))
         parts.append(('pos_idx', pos_idx if pos_idx.size else np.zeros(1, np.int32), np.int32))
@@ -310,12 +345,14 @@ class NarEngine:
         copied = torch.cuda.Event()
         copied.record(copy_stream)
         self._pin_events[slot] = copied
+        self._last_copied = copied
         tens = {}
         for name, (o, nel, dt, shp) in offs.items():
             tens[name] = dev[o:o + nel * np.dtype(dt).itemsize].view(_NP2T[dt]).view(*shp) if nel > 0 else \
                 torch.zeros(shp, dtype=_NP2T[dt], device=self.dev)
         return {'t': tens, 'Bg': Bg, 'B': per, 'T': T, 'L': L, 'L_global': L_global, 's0': s0,
-                'h2d_bytes': total, 'lens': lens, 'slot': slot}
+                'h2d_bytes': total, 'lens': lens, 'slot': slot, 'dstate': use_dstate, 'has_clicks': bool(all_items.any()),
+                'copied': copied}
 
     # ------------------------------------------------------------------ feature plan (static part)
     def _plan_c_static(self) -> FeaturePlanC:
@@ -368,7 +405,7 @@ class NarEngine:
             p.ctx_int[i] = t['ci/' + n].data_ptr()
         for i, n in enumerate(self.plan.ctx_float_names):
             p.ctx_float[i] = t['cf/' + n].data_ptr()
-        p.pop_norm = t['pop_norm'].data_ptr()
+        p.pop_norm = st['prep']['io'].pop_norm
         p.stats = self.buffer(st, 'stats').data_ptr()
         return p
 
@@ -383,7 +420,13 @@ class NarEngine:
         io.train = 1                        # the carve of a training step is a superset: evaluation reuses the same offsets
         io.all_items, io.event_ts = t['all_items'].data_ptr(), t['event_ts'].data_ptr()
         io.item_clicked, io.label_next = t['item_clicked'].data_ptr(), t['label_next'].data_ptr()
-        io.buffer, io.max_ts, io.pop_norm = t['buffer'].data_ptr(), t['max_ts'].data_ptr(), t['pop_norm'].data_ptr()
+        if st.get('dstate'):
+            # the state as of NOW: every update of an earlier batch has been queued (stream order does the rest)
+            buf_t, pop_t = self.dstate.buffer_ids(), self.dstate.articles_recent_pop_norm()
+            st['_hold_state'] = (buf_t, pop_t)
+        else:
+            buf_t, pop_t = t['buffer'], t['pop_norm']
+        io.buffer, io.max_ts, io.pop_norm = buf_t.data_ptr(), t['max_ts'].data_ptr(), pop_t.data_ptr()
         for i, n in enumerate(self.plan.ctx_int_names):
             io.ctx_int[i] = t['ci/' + n].data_ptr()
         for i, n in enumerate(self.plan.ctx_float_names):
@@ -485,9 +528,11 @@ class NarEngine:
                     neg=b('neg').view(-1)[st['s0'] * T * K:(st['s0'] + st['B']) * T * K].view(st['B'], T, K))
 
     def apply_gradients(self, st: Optional[dict] = None):
-        """NCCL sum-allreduce of the flat gradient buffer (data parallel), then TF-Adam (one C call)."""
+        """NCCL sum-allreduce of the flat gradient buffer + loss accumulators (data parallel: ONE collective per step), then
+        TF-Adam (one C call)."""
         if self.world > 1:
-            torch.distributed.all_reduce(self.grads, group=self.pg)
+            torch.distributed.all_reduce(self._grads_ext, group=self.pg)
+            self._loss_reduced = True
         io = st['prep']['io'] if st is not None and st.get('prep') else StepIO()
         io.global_step = self.global_step
         self._sync_cfg()
@@ -519,14 +564,29 @@ class NarEngine:
             return self.prepare(st, self.global_step + 1, stream=side)
         return self.stage(features, labels, buffer, pop_norm, slot=slot)
 
+    def stage_ahead_device_state(self, features, labels, slot: str, prev: Optional[dict],
+                                 after: Optional[torch.cuda.Event] = None) -> dict:
+        """``stage_ahead`` with the device-resident state: on the side stream, first the state absorbs the PREVIOUS batch
+        (``prev`` = its staged dict; what the hook's after_run does on the host in the reference), then the new batch is
+        copied and its weight-independent front runs against the updated state."""
+        side = self.side_stream() if self.use_side_stream else torch.cuda.current_stream()
+        if after is not None and self.use_side_stream:
+            side.wait_event(after)
+        if prev is not None:
+            if self.use_side_stream and prev.get('copied') is not None:
+                side.wait_event(prev['copied'])
+            self.advance_device_state(prev, stream=side)
+        st = self.stage(features, labels, None, None, slot=slot, stream=side if self.use_side_stream else None)
+        if self.use_side_stream:
+            return self.prepare(st, self.global_step + 1, stream=side)
+        return st
+
     def submit(self, st: dict, keep: bool = False) -> dict:
         """Queue one training step; nothing here waits for the GPU.  ``result(out)`` later waits for THIS step only
         (event), so the caller may queue step n+1 before reading the loss of step n - no bubble between steps."""
         out = self.step(st, train=True, keep=keep)
         if st['L'] > 0 or self.world > 1:
-            self.apply_gradients(st)
-        if self.world > 1:
-            torch.distributed.all_reduce(self.loss_dev, group=self.pg)
+            self.apply_gradients(st)                  # (the loss accumulators ride along with the gradients)
         self._loss_slot ^= 1
         host = self._loss_hosts[self._loss_slot]
         host.copy_(self.loss_dev, non_blocking=True)
@@ -587,9 +647,7 @@ class NarEngine:
         st = self.stage(features, labels, buffer, pop_norm)
         out = self.step(st, train=True, keep=keep)
         if st['L'] > 0 or self.world > 1:
-            self.apply_gradients(st)
-        if self.world > 1:
-            torch.distributed.all_reduce(self.loss_dev, group=self.pg)
+            self.apply_gradients(st)                  # (the loss accumulators ride along with the gradients)
         self.loss_host.copy_(self.loss_dev, non_blocking=True)
         out['stage'] = st
         if sync:

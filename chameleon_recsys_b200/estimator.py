@@ -13,6 +13,7 @@ the model object is cached across ``train()`` calls instead of being rebuilt fro
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Callable, Dict, List, Optional
 
@@ -116,6 +117,7 @@ class Estimator:
         self._eval_spec: Optional[EstimatorSpec] = None
         self.last_loss = None
         self.interactions = 0
+        self.h2d_bytes_per_step = 0
 
     def _ensure_spec(self, features, labels) -> EstimatorSpec:
         if self._spec is None:
@@ -169,8 +171,18 @@ class Estimator:
         eng = spec.model.engine
         for h in spec.training_chief_hooks:
             h.begin()
-        feed = feed_of(spec)
-        st_next = eng.stage_ahead(nxt[0], nxt[1], feed['pop_recent_items_buffer'], feed['articles_recent_pop_norm'], 'pipe0')
+        # Device-resident ClickedItemsState (default; NAR_DEVICE_STATE=0 keeps the hook's host update + per-step upload):
+        # the recent-clicks buffer / popularity live in HBM for the duration of train() and are advanced by one kernel per
+        # step on the side stream (what hook.after_run does on the host, nar_model.py:1635-1650); the host object is
+        # brought up to date when train() returns.
+        use_ds = os.environ.get('NAR_DEVICE_STATE', '1') == '1' and self._state() is not None
+        prev_st = None
+        if use_ds:
+            eng.attach_device_state(self._state())
+            st_next = eng.stage_ahead_device_state(nxt[0], nxt[1], 'pipe0', None)
+        else:
+            feed = feed_of(spec)
+            st_next = eng.stage_ahead(nxt[0], nxt[1], feed['pop_recent_items_buffer'], feed['articles_recent_pop_norm'], 'pipe0')
         pending = None                                              # (features, labels, out) of the step whose loss is unread
 
         def finish(p):
@@ -183,23 +195,33 @@ class Estimator:
         while nxt is not None:
             features, labels = nxt
             out = eng.submit(st_next)                               # step n queued on the main stream
-            run_values = {'clicked_items': features['item_clicked'], 'clicked_timestamps': features['event_timestamp'],
-                          'last_item_label': labels['label_last_item']}
-            for h in spec.training_chief_hooks:
-                h.after_run(None, run_values)                        # host state now describes "before step n+1"
+            prev_st = st_next
+            self.h2d_bytes_per_step = st_next['h2d_bytes']           # bytes of the one pinned H2D copy of this step
+            if not use_ds:
+                run_values = {'clicked_items': features['item_clicked'], 'clicked_timestamps': features['event_timestamp'],
+                              'last_item_label': labels['label_last_item']}
+                for h in spec.training_chief_hooks:
+                    h.after_run(None, run_values)                    # host state now describes "before step n+1"
             n += 1
             nxt = fetch() if (steps is None or n < steps) else None
             if nxt is not None:
-                feed = feed_of(spec)
                 # slot (n & 1) was last read by step n-1 (= pending): its event gates the side-stream copy
-                st_next = eng.stage_ahead(nxt[0], nxt[1], feed['pop_recent_items_buffer'],
-                                          feed['articles_recent_pop_norm'], 'pipe%d' % (n & 1),
-                                          after=pending[2]['done'] if pending is not None else None)
+                after = pending[2]['done'] if pending is not None else None
+                if use_ds:
+                    st_next = eng.stage_ahead_device_state(nxt[0], nxt[1], 'pipe%d' % (n & 1), prev_st, after=after)
+                else:
+                    feed = feed_of(spec)
+                    st_next = eng.stage_ahead(nxt[0], nxt[1], feed['pop_recent_items_buffer'],
+                                              feed['articles_recent_pop_norm'], 'pipe%d' % (n & 1), after=after)
+            elif use_ds:
+                eng.advance_device_state(prev_st)                    # the last batch of this train() call
             if pending is not None:
                 finish(pending)                                      # loss of step n-1: the GPU already runs step n
             pending = (features, labels, out)
         if pending is not None:
             finish(pending)
+        if use_ds:
+            eng.detach_device_state()                                # host ClickedItemsState = the device state (sync)
         for h in spec.training_chief_hooks:
             h.end()
         if self.model_dir:

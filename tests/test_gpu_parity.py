@@ -351,6 +351,37 @@ def test_estimator_evaluate_roundtrip():
     assert est._eval_spec.model.predicted_item_ids.shape[1] == 1 + k_eval
 
 
+def test_device_resident_state_training_loop(monkeypatch):
+    """Estimator.train with the recent-clicks state in HBM (default) == the loop with the hook's host update and per-step
+    upload: same negatives (so same buffer at every step), same losses to float-atomics noise, identical host state
+    afterwards (buffer, popularity counters, float64 pop-norm), and a smaller per-step H2D copy."""
+    import copy
+    import torch
+    from chameleon_recsys_b200.estimator import build_estimator
+    from chameleon_recsys_b200.harness import make_problem, warm_state
+    runs = {}
+    for mode in ('1', '0'):
+        monkeypatch.setenv('NAR_DEVICE_STATE', mode)
+        pb = make_problem('tiny', profile='B')
+        warm_state(pb, 5)
+        est = build_estimator(None, pb.content_article_embeddings_matrix, pb.articles_metadata, pb.articles_features_config,
+                              pb.session_features_config, pb.hp, pb.clicked_items_state)
+        losses = []
+        for rep in range(2):                                     # two train() calls: attach / detach twice
+            it = pb.input_fn()
+            est.train(lambda: it, steps=6)
+            losses.append(est.last_loss)
+        st = pb.clicked_items_state
+        runs[mode] = (losses, est.model.engine.params.clone(), copy.deepcopy(st.pop_recent_clicks_buffer),
+                      st.get_articles_recent_pop_norm().copy(), st.get_articles_pop().copy(), est.h2d_bytes_per_step)
+    a, b = runs['1'], runs['0']
+    for x, y in zip(a[0], b[0]):
+        assert abs(x - y) / abs(y) < 1e-4
+    assert float((a[1] - b[1]).abs().median()) < 1e-6
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
+    assert a[5] < b[5]
+
+
 def test_checkpoint_resume_matches_uninterrupted_run(tmp_path):
     """A checkpoint restores weights, TF-Adam slots, step and host state EXACTLY; training on from it tracks the run
     that was never interrupted (to float-atomics noise: Adam turns a +-1e-12 "zero" gradient into a +-lr update, so

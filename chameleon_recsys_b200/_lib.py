@@ -62,6 +62,7 @@ class ModelCfg(C.Structure):
                 ('off_gamma', C.c_int64), ('off_beta', C.c_int64),
                 ('off_M', C.c_int64 * 4), ('off_c', C.c_int64 * 4), ('ld_M', C.c_int64 * 4),
                 ('off_Wx', C.c_int64 * NAR_MAX_LAYERS), ('off_Wh', C.c_int64 * NAR_MAX_LAYERS), ('off_rb', C.c_int64 * NAR_MAX_LAYERS),
+                ('off_Wxc', C.c_int64 * NAR_MAX_LAYERS), ('off_Whc', C.c_int64 * NAR_MAX_LAYERS), ('off_bc', C.c_int64 * NAR_MAX_LAYERS),
                 ('plan', FeaturePlanC)]
 
 
@@ -122,6 +123,8 @@ _SIGNATURES = {
                                 C.POINTER(GemmEpilogue), vp]),
     'nar_ugrnn_fwd': (C.c_int, [vp, vp, vp, vp, i64, i64, vp, vp, vp, vp]),
     'nar_ugrnn_bwd': (C.c_int, [vp, vp, vp, vp, vp, vp, vp, i64, i64, vp, vp, vp]),
+    'nar_gru_fwd': (C.c_int, [vp, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp]),
+    'nar_gru_bwd': (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp, vp, vp]),
     'nar_sample_negatives_workspace': (C.c_int, [i64, i64, i64, i64, C.POINTER(i64)]),
     'nar_sample_negatives': (C.c_int, [vp, vp, i64, i64, i64, i64, vp, i64, i64, i64, u64, u32, vp, vp, i64, vp]),
     'nar_mul_pred': (C.c_int, [vp, vp, i64, i64, i64, vp, vp]),

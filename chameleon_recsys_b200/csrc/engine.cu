@@ -48,7 +48,8 @@ struct PrepBufs {
 struct StepBufs {
   float *X, *dX, *H1, *E, *dE, *dH1, *F1, *PR, *logits, *PD, *dPD, *Z1, *Z2, *Z3, *dZ1, *dZ2, *dZ3, *dPR, *dF1, *dHO;
   float *GX[NAR_MAX_LAYERS], *HO[NAR_MAX_LAYERS], *GT[NAR_MAX_LAYERS], *CD[NAR_MAX_LAYERS], *dGX[NAR_MAX_LAYERS],
-        *HPV[NAR_MAX_LAYERS], *dHOb[NAR_MAX_LAYERS], *HOd[NAR_MAX_LAYERS];   // HOd: RNN outputs after DropoutWrapper
+        *HPV[NAR_MAX_LAYERS], *dHOb[NAR_MAX_LAYERS], *HOd[NAR_MAX_LAYERS],   // HOd: RNN outputs after DropoutWrapper
+        *UO[NAR_MAX_LAYERS], *RH[NAR_MAX_LAYERS];                          // GRU: update gate, r * previous state
   float *PP, *PI, *PC, *DB;        // dedup: layer-1 pre-activations and their gradients
 };
 
@@ -61,6 +62,7 @@ struct nar_engine {
   cudaEvent_t ev[N_EVENTS];
   int ev_i;
   float* WhT[NAR_MAX_LAYERS];
+  float* WhcT[NAR_MAX_LAYERS];     // GRU: transposed candidate recurrent block
   int64_t launches;
 };
 
@@ -97,9 +99,11 @@ int64_t step_carve(const nar_engine* e, int64_t L_cap, int train, void* base, St
   if (c.dedup) { sb->X = cv.take<float>(NB * Fp); } else { sb->X = cv.take<float>(R * Fp); }
   sb->H1 = cv.take<float>(R * C);
   sb->E = cv.take<float>(R * C);
+  const int64_t gw = c.rnn_cell == 1 ? 3 : 2;           // gate blocks per unit: UGRNN (gate | candidate), GRU (r | u | candidate)
   for (int i = 0; i < c.layers; ++i) {
-    sb->GX[i] = cv.take<float>(L_cap * 2 * Hp); sb->HO[i] = cv.take<float>(L_cap * Hp);
+    sb->GX[i] = cv.take<float>(L_cap * gw * Hp); sb->HO[i] = cv.take<float>(L_cap * Hp);
     sb->GT[i] = cv.take<float>(L_cap * Hp); sb->CD[i] = cv.take<float>(L_cap * Hp);
+    if (c.rnn_cell == 1) { sb->UO[i] = cv.take<float>(L_cap * Hp); sb->RH[i] = cv.take<float>(L_cap * Hp); }
   }
   sb->F1 = cv.take<float>(L_cap * 512);
   sb->PR = cv.take<float>(L_cap * C);
@@ -112,7 +116,7 @@ int64_t step_carve(const nar_engine* e, int64_t L_cap, int train, void* base, St
     sb->dE = cv.take<float>(R * C);
     sb->dPR = cv.take<float>(L_cap * C); sb->dF1 = cv.take<float>(L_cap * 512); sb->dHO = cv.take<float>(L_cap * Hp);
     for (int i = 0; i < c.layers; ++i) {
-      sb->dGX[i] = cv.take<float>(L_cap * 2 * Hp); sb->HPV[i] = cv.take<float>(L_cap * Hp); sb->dHOb[i] = cv.take<float>(L_cap * Hp);
+      sb->dGX[i] = cv.take<float>(L_cap * gw * Hp); sb->HPV[i] = cv.take<float>(L_cap * Hp); sb->dHOb[i] = cv.take<float>(L_cap * Hp);
     }
     if (c.ranking == 0) {
       sb->dZ3 = cv.take<float>(Rc * 32); sb->dZ2 = cv.take<float>(Rc * 64); sb->dZ1 = cv.take<float>(Rc * 128); sb->dPD = cv.take<float>(Rc * C);
@@ -228,8 +232,16 @@ int run_step(nar_engine* e, const nar_step_io* io, cudaStream_t main) {
   auto session_branch = [&](cudaStream_t st) {
     const float* rnn_in = sb.E; int64_t n_in = C;
     for (int i = 0; i < c.layers; ++i) {
+      if (c.rnn_cell == 1) {
+        // GRUCell: gx = (x Wxg + bg | x Wxc + bc), then the recurrence (csrc/gru.cu)
+        s.fwd(rnn_in, i == 0 ? C : Hp, c.off_Wx[i], 2 * Hp, c.off_rb[i], sb.GX[i], 3 * Hp, L, 2 * Hp, n_in, NAR_ACT_NONE, st);
+        s.fwd(rnn_in, i == 0 ? C : Hp, c.off_Wxc[i], Hp, c.off_bc[i], sb.GX[i] + 2 * Hp, 3 * Hp, L, Hp, n_in, NAR_ACT_NONE, st);
+        s.chk(nar_gru_fwd(e->ctx, sb.GX[i], s.W(c.off_Wh[i]), s.W(c.off_Whc[i]), io->sess_off, B, Hp, sb.HO[i], sb.GT[i], sb.UO[i],
+                          sb.CD[i], sb.RH[i], st));
+      } else {
       s.fwd(rnn_in, i == 0 ? C : Hp, c.off_Wx[i], 2 * Hp, c.off_rb[i], sb.GX[i], 2 * Hp, L, 2 * Hp, n_in, NAR_ACT_NONE, st);
       s.chk(nar_ugrnn_fwd(e->ctx, sb.GX[i], s.W(c.off_Wh[i]), io->sess_off, B, Hp, sb.HO[i], sb.GT[i], sb.CD[i], st));
+      }
       // DropoutWrapper(output_keep_prob) (nar_model.py:1330-1333): the cell's OUTPUT is dropped, its state is not
       if (drop) dropout(sb.HO[i], sb.HOd[i], L, Hp, io->pos_idx, 8 + i, st);
       rnn_in = drop ? sb.HOd[i] : sb.HO[i]; n_in = Hp;
@@ -302,10 +314,35 @@ int run_step(nar_engine* e, const nar_step_io* io, cudaStream_t main) {
   float* dho = sb.dHO;
   for (int i = c.layers - 1; i >= 0; --i) {
     if (drop) dropout(dho, dho, L, Hp, io->pos_idx, 8 + i, main);       // gradient of the dropped cell output
-    s.chk(nar_transpose_f32(s.W(c.off_Wh[i]), Hp, 2 * Hp, 2 * Hp, e->WhT[i], Hp, main));
-    s.chk(nar_ugrnn_bwd(e->ctx, dho, sb.HO[i], sb.GT[i], sb.CD[i], e->WhT[i], io->sess_off, B, Hp, sb.dGX[i], sb.HPV[i], main));
     const float* x_in = i == 0 ? sb.E : (drop ? sb.HOd[i - 1] : sb.HO[i - 1]);
     const int64_t n_in = i == 0 ? C : Hp;
+    if (c.rnn_cell == 1) {
+      const int64_t W3 = 3 * Hp;
+      s.chk(nar_transpose_f32(s.W(c.off_Wh[i]), Hp, 2 * Hp, 2 * Hp, e->WhT[i], Hp, main));
+      s.chk(nar_transpose_f32(s.W(c.off_Whc[i]), Hp, Hp, Hp, e->WhcT[i], Hp, main));
+      s.chk(nar_gru_bwd(e->ctx, dho, sb.HO[i], sb.GT[i], sb.UO[i], sb.CD[i], e->WhT[i], e->WhcT[i], io->sess_off, B, Hp, sb.dGX[i],
+                        sb.HPV[i], main));
+      const float* dg = sb.dGX[i]; const float* dc = sb.dGX[i] + 2 * Hp;
+      {
+        cudaStream_t st = s.fork();
+        s.wgrad(x_in, n_in, dg, W3, c.off_Wx[i], 2 * Hp, n_in, 2 * Hp, L, st);
+        s.wgrad(x_in, n_in, dc, W3, c.off_Wxc[i], Hp, n_in, Hp, L, st);
+        s.wgrad(sb.HPV[i], Hp, dg, W3, c.off_Wh[i], 2 * Hp, Hp, 2 * Hp, L, st);
+        s.wgrad(sb.RH[i], Hp, dc, W3, c.off_Whc[i], Hp, Hp, Hp, L, st);
+        s.bgrad(dg, W3, L, 2 * Hp, c.off_rb[i], st);
+        s.bgrad(dc, W3, L, Hp, c.off_bc[i], st);
+      }
+      // d(input) = d_gx[:, :2Hp] Wxg^T + d_gx[:, 2Hp:] Wxc^T (two GEMMs into one buffer), then through the CAR tanh for layer 0
+      float* dxin = i == 0 ? sb.dE : sb.dHOb[i];
+      const int64_t ldx = i == 0 ? C : Hp;
+      s.dgrad(dg, W3, c.off_Wx[i], 2 * Hp, dxin, ldx, L, n_in, 2 * Hp, NAR_ACT_NONE, nullptr, 0, 0, main);
+      s.dgrad(dc, W3, c.off_Wxc[i], Hp, dxin, ldx, L, n_in, Hp, NAR_ACT_NONE, nullptr, 0, 1, main);
+      if (i == 0) s.chk(nar_act_bwd(sb.dE, sb.E, L * C, NAR_ACT_TANH, sb.dE, main));
+      else dho = sb.dHOb[i];
+      continue;
+    }
+    s.chk(nar_transpose_f32(s.W(c.off_Wh[i]), Hp, 2 * Hp, 2 * Hp, e->WhT[i], Hp, main));
+    s.chk(nar_ugrnn_bwd(e->ctx, dho, sb.HO[i], sb.GT[i], sb.CD[i], e->WhT[i], io->sess_off, B, Hp, sb.dGX[i], sb.HPV[i], main));
     {
       cudaStream_t st = s.fork();
       s.wgrad(x_in, n_in, sb.dGX[i], 2 * Hp, c.off_Wx[i], 2 * Hp, n_in, 2 * Hp, L, st);
@@ -353,7 +390,7 @@ int run_step(nar_engine* e, const nar_step_io* io, cudaStream_t main) {
 extern "C" int nar_engine_create(nar_ctx* ctx, const nar_model_cfg* cfg, nar_engine** out) {
   if (!ctx || !cfg || !out) return NAR_ERR_INVALID;
   *out = nullptr;
-  if (cfg->layers < 1 || cfg->layers > NAR_MAX_LAYERS || cfg->rnn_cell != 0 || cfg->ranking < 0 || cfg->ranking > 1)
+  if (cfg->layers < 1 || cfg->layers > NAR_MAX_LAYERS || cfg->rnn_cell < 0 || cfg->rnn_cell > 1 || cfg->ranking < 0 || cfg->ranking > 1)
     return NAR_ERR_UNSUPPORTED;
   if ((cfg->C & 3) || (cfg->Hp & 3) || (cfg->Fp & 3) || (cfg->ctx_col0 & 3) || cfg->ctx_col0 <= 0 || cfg->ctx_col0 >= cfg->Fp)
     return NAR_ERR_INVALID;
@@ -365,8 +402,10 @@ extern "C" int nar_engine_create(nar_ctx* ctx, const nar_model_cfg* cfg, nar_eng
   if (cudaStreamCreateWithFlags(&e->aux, cudaStreamNonBlocking) != cudaSuccess) { delete e; return NAR_ERR_NO_DEVICE; }
   for (int i = 0; i < N_EVENTS; ++i)
     if (cudaEventCreateWithFlags(&e->ev[i], cudaEventDisableTiming) != cudaSuccess) { delete e; return NAR_ERR_NO_DEVICE; }
-  for (int i = 0; i < cfg->layers; ++i)
+  for (int i = 0; i < cfg->layers; ++i) {
     if (cudaMalloc(&e->WhT[i], (size_t)2 * cfg->Hp * cfg->Hp * sizeof(float)) != cudaSuccess) { delete e; return NAR_ERR_NO_DEVICE; }
+    if (cfg->rnn_cell == 1 && cudaMalloc(&e->WhcT[i], (size_t)cfg->Hp * cfg->Hp * sizeof(float)) != cudaSuccess) { delete e; return NAR_ERR_NO_DEVICE; }
+  }
   *out = e;
   return NAR_OK;
 }
@@ -374,7 +413,7 @@ extern "C" int nar_engine_create(nar_ctx* ctx, const nar_model_cfg* cfg, nar_eng
 extern "C" int nar_engine_destroy(nar_engine* e) {
   if (!e) return NAR_OK;
   cudaStreamSynchronize(e->aux);
-  for (int i = 0; i < NAR_MAX_LAYERS; ++i) if (e->WhT[i]) cudaFree(e->WhT[i]);
+  for (int i = 0; i < NAR_MAX_LAYERS; ++i) { if (e->WhT[i]) cudaFree(e->WhT[i]); if (e->WhcT[i]) cudaFree(e->WhcT[i]); }
   for (int i = 0; i < N_EVENTS; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   if (e->aux) cudaStreamDestroy(e->aux);
   delete e;

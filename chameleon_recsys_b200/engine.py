@@ -41,8 +41,11 @@ class NarEngine:
                  dropout_seed: Optional[int] = None):
         if not torch.cuda.is_available():
             raise NarError('NarEngine needs a CUDA (sm_100a) device; there is no CPU fallback')
-        if rnn_cell != 'ugrnn':
-            raise NotImplementedError("rnn_cell=%r: only the reference's UGRNNCell is implemented" % rnn_cell)
+        if rnn_cell not in ('ugrnn', 'gru'):
+            raise ValueError("rnn_cell=%r: 'ugrnn' (the reference's UGRNNCell, nar_model.py:1318) or 'gru' (GRUCell, :1315)" % rnn_cell)
+        if rnn_cell != getattr(layout, 'rnn_cell', 'ugrnn'):
+            raise ValueError('ParamLayout was built for rnn_cell=%r' % getattr(layout, 'rnn_cell', 'ugrnn'))
+        self.rnn_cell = rnn_cell
         if ranking not in ('mlp', 'cosine'):
             raise ValueError(ranking)
         self.dev = torch.device('cuda', torch.cuda.current_device() if device is None else device)
@@ -138,7 +141,7 @@ class NarEngine:
         lay, pl = self.layout, self.plan
         c = ModelCfg()
         c.num_items, c.C, c.Hp, c.Fp, c.ctx_col0 = self.V, self.C, self.Hp, pl.Fp, pl.ctx_col0
-        c.layers, c.rnn_cell, c.ranking = self.layers, 0, 0 if self.ranking == 'mlp' else 1
+        c.layers, c.rnn_cell, c.ranking = self.layers, 1 if self.rnn_cell == 'gru' else 0, 0 if self.ranking == 'mlp' else 1
         c.fwd_precision, c.bwd_precision = self.fwd_prec, self.bwd_prec
         c.dedup, c.use_aux_stream = int(self.dedup), int(self.use_aux_stream)
         c.keep_prob, c.novelty_reg_factor = self.keep_prob, self.nov_factor
@@ -159,6 +162,8 @@ class NarEngine:
             c.off_M[i], c.off_c[i], c.ld_M[i] = off('M%d' % (i + 1)), off('c%d' % (i + 1)), lay.by_key['M%d' % (i + 1)].ld
         for i in range(self.layers):
             c.off_Wx[i], c.off_Wh[i], c.off_rb[i] = off('rnn%d/Wx' % i), off('rnn%d/Wh' % i), off('rnn%d/b' % i)
+            if self.rnn_cell == 'gru':
+                c.off_Wxc[i], c.off_Whc[i], c.off_bc[i] = off('rnn%d/Wxc' % i), off('rnn%d/Whc' % i), off('rnn%d/bc' % i)
         c.plan = self._plan_c_static()
         return c
 

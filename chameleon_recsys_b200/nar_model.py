@@ -71,7 +71,7 @@ class NARModuleModel:
         self.plan = FeaturePlan(session_features_config, articles_features_config, internal_features_config,
                                 max_cardinality_for_ohe, content_article_embeddings_matrix.shape[1],
                                 self.items_vocab_size)
-        self.layout = ParamLayout(self.plan, CAR_embedding_size, rnn_units, rnn_num_layers)
+        self.layout = ParamLayout(self.plan, CAR_embedding_size, rnn_units, rnn_num_layers, rnn_cell=rnn_cell)
         self.engine = NarEngine(self.plan, self.layout, content_article_embeddings_matrix, articles_metadata,
                                 negative_samples=negative_samples,
                                 negative_sample_from_buffer=negative_sample_from_buffer,

@@ -208,8 +208,10 @@ class ParamTensor:
 class ParamLayout:
     """Flat-buffer layout.  ``tensors`` in buffer order; regularised ones first."""
 
-    def __init__(self, plan: FeaturePlan, CAR_embedding_size: int, rnn_units: int, rnn_num_layers: int):
+    def __init__(self, plan: FeaturePlan, CAR_embedding_size: int, rnn_units: int, rnn_num_layers: int,
+                 rnn_cell: str = 'ugrnn'):
         self.plan = plan
+        self.rnn_cell = rnn_cell
         C = int(CAR_embedding_size)
         H = int(rnn_units)
         self.C, self.H, self.layers = C, H, int(rnn_num_layers)
@@ -250,7 +252,26 @@ class ParamLayout:
         noreg.append(ParamTensor('b2', 'main/CAR/CAR_representation/bias', (C,), INIT_ZEROS, False, rows=1, ld=C))
         # nar_model.py:1308-1342  (tf.contrib.rnn.UGRNNCell: kernel [in+H, 2H], bias [2H]; not regularised)
         gate_cols = np.concatenate([np.arange(H), Hp + np.arange(H)])
-        for i in range(self.layers):
+        for i in range(self.layers if rnn_cell == 'gru' else 0):
+            # tf.nn.rnn_cell.GRUCell (nar_model.py:1315, commented alternative): gates/kernel [in+H, 2H] (r | u), gates/bias
+            # (constant 1.0), candidate/kernel [in+H, H], candidate/bias (zeros); split into input and recurrent blocks
+            n_in = C if i == 0 else H
+            n_in_p = C if i == 0 else Hp
+            base = 'main/RNN/rnn/multi_rnn_cell/cell_{}/gru_cell/'.format(i)
+            gk, ck = base + 'gates/kernel', base + 'candidate/kernel'
+            noreg.append(ParamTensor('rnn%d/Wx' % i, gk, (n_in + H, 2 * H), INIT_XAVIER, False, rows=n_in_p, ld=2 * Hp,
+                                     col_map=gate_cols, part_of=gk, part_rows=(0, n_in), row_map=np.arange(n_in)))
+            noreg.append(ParamTensor('rnn%d/Wh' % i, gk, (n_in + H, 2 * H), INIT_XAVIER, False, rows=Hp, ld=2 * Hp,
+                                     col_map=gate_cols, part_of=gk, part_rows=(n_in, n_in + H), row_map=np.arange(H)))
+            noreg.append(ParamTensor('rnn%d/b' % i, base + 'gates/bias', (2 * H,), INIT_ONES, False, rows=1, ld=2 * Hp,
+                                     col_map=gate_cols))
+            noreg.append(ParamTensor('rnn%d/Wxc' % i, ck, (n_in + H, H), INIT_XAVIER, False, rows=n_in_p, ld=Hp,
+                                     col_map=np.arange(H), part_of=ck, part_rows=(0, n_in), row_map=np.arange(n_in)))
+            noreg.append(ParamTensor('rnn%d/Whc' % i, ck, (n_in + H, H), INIT_XAVIER, False, rows=Hp, ld=Hp,
+                                     col_map=np.arange(H), part_of=ck, part_rows=(n_in, n_in + H), row_map=np.arange(H)))
+            noreg.append(ParamTensor('rnn%d/bc' % i, base + 'candidate/bias', (H,), INIT_ZEROS, False, rows=1, ld=Hp,
+                                     col_map=np.arange(H)))
+        for i in range(self.layers if rnn_cell != 'gru' else 0):
             n_in = C if i == 0 else H
             n_in_p = C if i == 0 else Hp
             base = 'main/RNN/rnn/multi_rnn_cell/cell_{}/ugrnn_cell/'.format(i)

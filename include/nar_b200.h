@@ -189,6 +189,17 @@ int nar_ugrnn_bwd(nar_ctx* ctx, const float* d_hout /*[L,Hp]*/, const float* h_o
                   const float* cand, const float* WhT /*[2Hp,Hp]*/, const int32_t* sess_off, int64_t B,
                   int64_t Hp, float* d_gx /*[L,2Hp]*/, float* h_prev /*[L,Hp]*/, void* stream);
 
+/* GRU recurrence (tf.nn.rnn_cell.GRUCell; rnn_cell='gru'): gx [L,3Hp] = x*Wxg + bg | x*Wxc + bc (r | u | c pre-activations
+ * of the input), Whg [Hp,2Hp], Whc [Hp,Hp]:  [r,u] = sigmoid(gx_ru + h*Whg) ; c = tanh(gx_c + (r*h)*Whc) ;
+ * h' = u*h + (1-u)*c.  Outputs per row: state h_out, gates r / u, candidate c, rh = r * (state entering the step).      */
+int nar_gru_fwd(nar_ctx* ctx, const float* gx, const float* Whg, const float* Whc, const int32_t* sess_off, int64_t B,
+                int64_t Hp, float* h_out, float* r_out, float* u_out, float* c_out, float* rh_out, void* stream);
+/* d_gx [L,3Hp] = dL/d(pre-activations); h_prev [L,Hp] = state entering the step (dWhg = h_prev^T d_gx[:, :2Hp],
+ * dWhc = rh^T d_gx[:, 2Hp:]); WhgT [2Hp,Hp], WhcT [Hp,Hp] are the transposed recurrent blocks.                        */
+int nar_gru_bwd(nar_ctx* ctx, const float* d_hout, const float* h_out, const float* r_out, const float* u_out,
+                const float* c_out, const float* WhgT, const float* WhcT, const int32_t* sess_off, int64_t B, int64_t Hp,
+                float* d_gx, float* h_prev, void* stream);
+
 /* ---- negative sampler (replaces nar_model.py:1220-1304: tf.random_shuffle x(2+clicks),
  *      tf.unique, unsorted_segment_min, tf.setdiff1d inside nested tf.map_fn).  RNG spec:
  *      oracle/sampler_ref.py.  all_items_global [Bg,T1] builds the pool; negatives are
@@ -332,7 +343,7 @@ int nar_tf32_lo(const float* x, int64_t n, float* lo, void* stream);
 typedef struct {
   /* dimensions */
   int64_t num_items, C /*CAR_embedding_size*/, Hp /*rnn_units padded to 4*/, Fp /*feature row width*/, ctx_col0;
-  int32_t layers, rnn_cell /*0 = UGRNNCell (nar_model.py:1318)*/, ranking /*0 = MLP scorer (:444-500), 1 = cosine*/;
+  int32_t layers, rnn_cell /*0 = UGRNNCell (nar_model.py:1318), 1 = GRUCell (:1315)*/, ranking /*0 = MLP scorer (:444-500), 1 = cosine*/;
   int32_t fwd_precision, bwd_precision;       /* nar_gemm_epilogue.precision of the forward / backward GEMMs */
   int32_t dedup;                              /* 1: per-unique-id CAR layer 1 (csrc/car.cu); 0: every candidate row materialised */
   int32_t use_aux_stream;                     /* 1: weight / bias gradients (and the forward session branch) on the auxiliary stream */
@@ -349,7 +360,8 @@ typedef struct {
   int64_t n_params, reg_end;
   int64_t off_W1, off_b1, off_W2, off_b2, off_W3, off_b3, off_W4, off_b4, off_gamma, off_beta;
   int64_t off_M[4], off_c[4], ld_M[4];        /* matching_dense_layer_1..4 kernels / biases, leading dimensions */
-  int64_t off_Wx[NAR_MAX_LAYERS], off_Wh[NAR_MAX_LAYERS], off_rb[NAR_MAX_LAYERS];
+  int64_t off_Wx[NAR_MAX_LAYERS], off_Wh[NAR_MAX_LAYERS], off_rb[NAR_MAX_LAYERS];     /* UGRNN: [in|H, 2Hp] (gate | candidate); GRU: gates (r | u) */
+  int64_t off_Wxc[NAR_MAX_LAYERS], off_Whc[NAR_MAX_LAYERS], off_bc[NAR_MAX_LAYERS];  /* GRU only: candidate blocks [in|H, Hp] */
   /* feature plan: static part (segments, tables, metadata, created_at_ts, gamma / beta, column map) */
   nar_feature_plan plan;
 } nar_model_cfg;

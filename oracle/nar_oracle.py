@@ -225,6 +225,18 @@ class NarOracle:
             inp = x[:, t]
             new_states = []
             for i in range(self.layers):
+                if self.rnn_cell == 'gru':
+                    # tf.nn.rnn_cell.GRUCell (the cell nar_model.py:1315 keeps commented out; north_star's "session GRU"):
+                    # [r, u] = sigmoid([x, h] Wg + bg) ; c = tanh([x, r*h] Wc + bc) ; h' = u*h + (1-u)*c
+                    base = 'main/RNN/rnn/multi_rnn_cell/cell_{}/gru_cell/'.format(i)
+                    gi = torch.cat([inp, states[i]], dim=1) @ self._p(base + 'gates/kernel') + self._p(base + 'gates/bias')
+                    r, u = torch.sigmoid(gi[:, :H]), torch.sigmoid(gi[:, H:])
+                    c = torch.tanh(torch.cat([inp, r * states[i]], dim=1) @ self._p(base + 'candidate/kernel') +
+                                   self._p(base + 'candidate/bias'))
+                    h = u * states[i] + (1.0 - u) * c
+                    new_states.append(h)
+                    inp = h if pos_key is None else self._dropout(h, 8 + i, pos_key[:, t])
+                    continue
                 base = 'main/RNN/rnn/multi_rnn_cell/cell_{}/ugrnn_cell/'.format(i)
                 m = torch.cat([inp, states[i]], dim=1) @ self._p(base + 'kernel') + self._p(base + 'bias')
                 g_act, c_act = m[:, :H], m[:, H:]

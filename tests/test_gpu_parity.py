@@ -81,20 +81,20 @@ def test_adam_colsum_l2():
     assert not _fails(gpu_diag.fam_misc())
 
 
-def _check_steps(res, grad_tol=3e-2):
+def _check_steps(res, grad_tol=3e-2, update_tol=0.2):
     for s in res['steps']:
         assert s['neg_equal'], 'negatives must be bit-exact'
         assert max(s['x_in'], s['x_pos'], s['x_neg']) < 1e-5, s
         assert max(s['e_in'], s['e_pos'], s['e_neg'], s['rnn'], s['pred']) < 2e-4, s
         assert s['logits_rel_max'] < 1e-3, s
         assert s['xe_rel'] < 1e-3 and s['total_rel'] < 1e-3, s
-        assert s['grad_rel_max'] < grad_tol, s['grad_rel']
+        assert s['grad_rel_max'] < grad_tol, sorted(s['grad_rel'].items(), key=lambda kv: -kv[1])[:6]
         if s['step'] > 1:          # at t = 1 Adam's update is lr*sign(g): a sign flip of a ~0 gradient is not an error
-            assert s['update_err_over_lr'] < 0.2, s
+            assert s['update_err_over_lr'] < update_tol, s
 
 
 @pytest.mark.parametrize('case', ['tinyA', 'tinyB', 'tinyB_cold', 'tinyB_cos', 'tinyB_2l', 'tinyB_nov', 'tinyB_cos_nov', 'tinyB_drop',
-                                  'tinyB_2l_drop', 'tinyB_pad'])
+                                  'tinyB_2l_drop', 'tinyB_pad', 'tinyB_gru', 'tinyB_gru_2l_drop', 'tinyB_gru_cos'])
 def test_full_step_parity_tiny(case):
     import torch
     from tools import gpu_step_check as g
@@ -107,12 +107,17 @@ def test_full_step_parity_tiny(case):
            'tinyB_2l_drop': ('B', 5, 2, dict(rnn_num_layers=2, dropout_keep_prob=0.7)),
            # two sessions, empty buffer: the candidate pool runs out, negatives are zero padded (the padding slot of
            # the per-unique-id layer 1 and its backward segment sum)
-           'tinyB_pad': ('B', 0, 2, dict(batch_size=2))}[case]
+           'tinyB_pad': ('B', 0, 2, dict(batch_size=2)),
+           # rnn_cell='gru' (north_star's "session GRU"; nar_model.py:1315)
+           'tinyB_gru': ('B', 5, 3, dict(rnn_cell='gru')),
+           'tinyB_gru_2l_drop': ('B', 5, 2, dict(rnn_cell='gru', rnn_num_layers=2, dropout_keep_prob=0.8)),
+           'tinyB_gru_cos': ('B', 5, 2, dict(rnn_cell='gru', ranking='cosine'))}[case]
     # the two-layer dropout case checks the mask plumbing (which output is dropped where, forward and backward): it runs
     # the backward GEMMs error-compensated so that a wrong mask cannot hide in TF32 noise
-    ekw = dict(bwd_precision=3) if case == 'tinyB_2l_drop' else None
+    ekw = dict(bwd_precision=3) if case in ('tinyB_2l_drop', 'tinyB_gru_2l_drop') else None
     res = g.run_case('tiny', cfg[0], cfg[1], cfg[2], hp_over=cfg[3], oracle_dtype=torch.float64, engine_kw=ekw)
-    _check_steps(res, grad_tol=2e-3 if ekw else 3e-2)
+    # (5 positions in the padding case: Adam turns the TF32 noise of near-zero gradients into larger relative updates)
+    _check_steps(res, grad_tol=2e-3 if ekw else 3e-2, update_tol=0.5 if case == 'tinyB_pad' else 0.2)
 
 
 @pytest.mark.parametrize('case', ['tinyB', 'tinyB_cold', 'g1'])

@@ -30,7 +30,7 @@ def make_oracle(pb, dtype=torch.float64):
                      popularity_smooth_log_base=hp.popularity_smooth_log_base,
                      CAR_embedding_size=hp.CAR_embedding_size, rnn_units=hp.rnn_units,
                      rnn_num_layers=hp.rnn_num_layers, max_cardinality_for_ohe=hp.max_cardinality_for_ohe,
-                     lr=hp.learning_rate, ranking=hp.ranking, dtype=dtype, keep_prob=hp.dropout_keep_prob,
+                     lr=hp.learning_rate, ranking=hp.ranking, rnn_cell=hp.rnn_cell, dtype=dtype, keep_prob=hp.dropout_keep_prob,
                      novelty_reg_factor=hp.novelty_reg_factor, dropout_seed=hp.sampler_seed, int2log=pb.plan.int2log)
 
 
@@ -43,7 +43,7 @@ def make_engine(pb, **kw):
                      recent_clicks_buffer_max_size=hp.recent_clicks_buffer_max_size,
                      recent_clicks_for_normalization=hp.recent_clicks_for_normalization,
                      elapsed_days_smooth_log_base=hp.elapsed_days_smooth_log_base,
-                     popularity_smooth_log_base=hp.popularity_smooth_log_base, ranking=hp.ranking,
+                     popularity_smooth_log_base=hp.popularity_smooth_log_base, ranking=hp.ranking, rnn_cell=hp.rnn_cell,
                      sampler_seed=hp.sampler_seed, keep_prob=hp.dropout_keep_prob, novelty_reg_factor=hp.novelty_reg_factor,
                      **kw)
 

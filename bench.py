@@ -229,7 +229,8 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return 0
-    pb = make_problem(args.workload, profile=args.profile, session_len=args.session_len, state_cls=ClickedItemsStateRef)
+    hp_over = {'batch_size': args.global_batch // args.gpus} if args.global_batch else {}
+    pb = make_problem(args.workload, profile=args.profile, session_len=args.session_len, state_cls=ClickedItemsStateRef, **hp_over)
     gb = pb.hp.batch_size * args.gpus
     # bounded sample: a step of this arm processes at most REF_STEP_SESSIONS sessions of the global batch (one oracle
     # step costs ~2.5 s of CPU work per 256 sessions), so that --steps K --warmup W ends within a few minutes at any N
@@ -284,7 +285,12 @@ def run_ours(args):
     if world != args.gpus:
         if rank == 0:
             print('warning: --gpus %d but WORLD_SIZE %d' % (args.gpus, world), file=sys.stderr)
-    pb = make_problem(args.workload, profile=args.profile, session_len=args.session_len)
+    hp_over = {}
+    if args.global_batch:
+        if args.global_batch % world:
+            raise SystemExit('--global-batch must be a multiple of the number of ranks')
+        hp_over['batch_size'] = args.global_batch // world
+    pb = make_problem(args.workload, profile=args.profile, session_len=args.session_len, **hp_over)
     hp = pb.hp
     gb = hp.batch_size * world
     warm_state(pb, args.state_warmup)
@@ -361,6 +367,39 @@ def run_ours(args):
     value = n_int / (ms_total * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
 
+    # ------------------------------------------------------------------ BASELINE configs[3]: G1-shaped, GLOBAL batch 4096 on 8 GPUs
+    # (512 sessions per GPU).  The scaling series keeps the per-GPU batch of configs[1] (weak scaling, 256 per GPU);
+    # this extra device-timed measurement reports the configuration BASELINE.json names, in the same line.
+    cfg3 = None
+    if world == 8 and args.workload == 'g1' and not args.global_batch and os.environ.get('NAR_BENCH_CFG3', '1') == '1':
+        pb3 = make_problem('g1', profile=args.profile, session_len=args.session_len, batch_size=512)
+        warm_state(pb3, 20)
+        w3, k3 = 3, 10
+        b3 = make_batches(pb3, w3 + k3, 512 * world)
+        est3 = build_estimator(None, pb3.content_article_embeddings_matrix, pb3.articles_metadata, pb3.articles_features_config,
+                               pb3.session_features_config, pb3.hp, pb3.clicked_items_state, process_group=pg, device=local_rank)
+        eng3 = est3._ensure_spec(None, None).model.engine
+        st3 = [eng3.stage(f, l, bu, po, slot='c3_%d' % i) for i, (f, l, bu, po) in enumerate(b3)]
+        torch.cuda.synchronize()
+        for i in range(w3):
+            eng3.step(st3[i], train=True); eng3.apply_gradients(st3[i])
+        barrier()
+        a3, z3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a3.record()
+        for i in range(w3, w3 + k3):
+            eng3.step(st3[i], train=True); eng3.apply_gradients(st3[i])
+            if i + 1 < len(st3):
+                eng3.prepare(st3[i + 1], eng3.global_step + 1, stream=eng3.side_stream())
+        z3.record()
+        barrier()
+        m3 = torch.tensor([a3.elapsed_time(z3)], device='cuda')
+        dist.all_reduce(m3, op=dist.ReduceOp.MAX)
+        n3 = sum(s['L_global'] for s in st3[w3:])
+        cfg3 = {'workload': 'BASELINE configs[3]: G1-shaped, global batch 4096 = 512 sessions per GPU, 8 GPUs', 'steps': k3, 'warmup': w3,
+                'value': n3 / (float(m3.item()) * 1e-3), 'unit': 'interactions/s', 'ms_per_step': float(m3.item()) / k3,
+                'interactions_per_step': n3 / k3}
+        del eng3, est3, st3
+
     # ------------------------------------------------------------------ e2e: Estimator API, host batches
     e2e_batches = batches[n_total:]
     h2d = []
@@ -435,6 +474,8 @@ def run_ours(args):
             'host_enqueue_ms_per_step': host_enqueue_ms, 'host_loop_ms_per_step_incl_waiting_for_the_gpu': host_loop_ms,
             'host_run_ahead_steps': depth,
             'roofline': roof, 'roofline_gather': roof_g, 'clocks': clocks}
+    if cfg3:
+        line['configs3_g1_batch4096_8gpu'] = cfg3
     if cpu:
         line['cpu_baseline'] = cpu
     emit(line)
@@ -554,6 +595,8 @@ def main():
     ap.add_argument('--state-warmup', type=int, default=100)
     ap.add_argument('--cpu-steps', type=int, default=5)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--global-batch', type=int, default=0,
+                    help='sessions per step over ALL ranks (per-GPU batch = this / world); 0 = the workload batch per GPU (weak scaling)')
     args = ap.parse_args()
     # the contract is ONE JSON line on stdout: libraries (NCCL prints its version banner there) get stderr instead
     global _REAL_STDOUT

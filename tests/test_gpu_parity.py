@@ -217,6 +217,19 @@ def test_nccl_two_ranks_match_single():
     assert res['param_diff_median'] < 1e-6 and res['param_diff_max'] <= 2.5 * res['steps'] * res['lr'], res
 
 
+@pytest.mark.parametrize('wl', ['adressa', 'stress'])
+def test_full_step_parity_other_baseline_shapes(wl):
+    """BASELINE configs[2] (Adressa-shaped: 13K items, K 100, seq <= 30, 5000 from the buffer) and configs[4] (stress: 1M
+    items, E 512, H 512, K 500) at a batch the fp32 oracle finishes in seconds: one full step, same bars."""
+    import torch
+    from tools import gpu_step_check as g
+    if wl == 'adressa':
+        res = g.run_case('adressa', 'B', 20, 1, hp_over=dict(batch_size=32), oracle_dtype=torch.float32)
+    else:
+        res = g.run_case('stress', 'B', 4, 1, hp_over=dict(batch_size=8), oracle_dtype=torch.float32)
+    _check_steps(res)
+
+
 def test_full_size_properties_g1():
     """BASELINE config[1] at full size over several steps: size-independent properties of every step."""
     import torch

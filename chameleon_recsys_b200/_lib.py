@@ -86,7 +86,7 @@ class NoveltyReg(C.Structure):
 class GemmEpilogue(C.Structure):
     _fields_ = [('bias', C.c_void_p), ('act', C.c_int32), ('dact', C.c_int32), ('aux', C.c_void_p),
                 ('ld_aux', C.c_int64), ('accumulate', C.c_int32), ('split_k', C.c_int32),
-                ('precision', C.c_int32), ('b_lo', C.c_void_p)]
+                ('precision', C.c_int32), ('b_lo', C.c_void_p), ('b_bf16', C.c_void_p), ('ld_bf16', C.c_int64)]
 
 
 _lib: Optional[C.CDLL] = None
@@ -113,6 +113,7 @@ _SIGNATURES = {
     'nar_engine_prepare': (C.c_int, [vp, C.POINTER(StepIO), vp]),
     'nar_engine_step': (C.c_int, [vp, C.POINTER(StepIO), vp]),
     'nar_engine_apply': (C.c_int, [vp, C.POINTER(StepIO), vp]),
+    'nar_engine_refresh': (C.c_int, [vp, vp]),
     'nar_engine_buffer': (C.c_int, [vp, C.POINTER(StepIO), C.c_char_p, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)]),
     'nar_engine_launch_count': (i64, [vp]),
     'nar_build_rows': (C.c_int, [vp, i64, vp, vp, vp, i64, vp, vp, vp]),
@@ -121,6 +122,7 @@ _SIGNATURES = {
     'nar_scatter_add_rows_f32': (C.c_int, [vp, i64, i64, C.c_int, vp, i64, vp, i64, vp]),
     'nar_gemm_tf32': (C.c_int, [vp, i64, i64, i64, vp, i64, C.c_int, vp, i64, C.c_int, vp, i64,
                                 C.POINTER(GemmEpilogue), vp]),
+    'nar_pack_bf16x3': (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, vp, vp]),
     'nar_ugrnn_fwd': (C.c_int, [vp, vp, vp, vp, i64, i64, vp, vp, vp, vp]),
     'nar_ugrnn_bwd': (C.c_int, [vp, vp, vp, vp, vp, vp, vp, i64, i64, vp, vp, vp]),
     'nar_gru_fwd': (C.c_int, [vp, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp]),

@@ -55,9 +55,21 @@ struct StepBufs {
 
 }  // namespace
 
+// bf16x3 planes of the forward weights (fwd_precision 4; see gemm_tcgen05.cu MODE 4): one entry per (weight block, K) a
+// forward GEMM uses; refreshed by one nar_pack_bf16x3 launch after every optimiser step / weight load
+constexpr int MAX_PLANES = 32;
+struct PlaneSet {
+  int n;
+  int64_t off_W[MAX_PLANES]; int32_t K[MAX_PLANES], N[MAX_PLANES], ldw[MAX_PLANES], ld_out[MAX_PLANES];
+  int64_t dst[MAX_PLANES];                 // element offset of the plane in `buf`
+  const float* W[MAX_PLANES]; void* out[MAX_PLANES];
+  uint16_t* buf; void* descs;
+};
+
 struct nar_engine {
   nar_ctx* ctx;
   nar_model_cfg cfg;
+  PlaneSet planes;
   cudaStream_t aux;
   cudaEvent_t ev[N_EVENTS];
   int ev_i;
@@ -164,12 +176,19 @@ struct Seq {
   const float* W(int64_t off) const { return c.params + off; }
   float* G(int64_t off) const { return c.grads + off; }
 
-  // Y[M,N] = act(X[M,Kd] * W[Kd,N] + b)      (W stored [in,out]: MN-major B operand)
+  // Y[M,N] = act(X[M,Kd] * W[Kd,N] + b)      (W stored [in,out]: MN-major B operand, or its bf16x3 plane)
   void fwd(const float* X, int64_t ldx, int64_t off_W, int64_t ldw, int64_t off_b, float* Y, int64_t ldy, int64_t M, int64_t N,
            int64_t Kd, int act, cudaStream_t st) {
     nar_gemm_epilogue ep; memset(&ep, 0, sizeof(ep));
     ep.bias = off_b >= 0 ? W(off_b) : nullptr; ep.act = act; ep.split_k = 1; ep.precision = c.fwd_precision;
     ep.b_lo = c.fwd_precision == 3 ? c.params_lo + off_W : nullptr;
+    if (c.fwd_precision == 4) {
+      const PlaneSet& ps = e->planes;
+      int i = 0;
+      for (; i < ps.n; ++i) if (ps.off_W[i] == off_W && ps.K[i] == Kd && ps.N[i] == N) break;
+      if (i == ps.n) { ep.precision = 3; ep.b_lo = c.params_lo + off_W; }      // no plane for this block: 3xTF32
+      else { ep.b_bf16 = ps.buf + ps.dst[i]; ep.ld_bf16 = ps.ld_out[i]; }
+    }
     chk(nar_gemm_tf32(e->ctx, M, N, Kd, X, ldx, 1, W(off_W), ldw, 0, Y, ldy, &ep, st));
   }
   // dX[M,n_in] (+)= dY[M,n_out] * W^T, optionally times act'(aux)
@@ -386,6 +405,43 @@ int run_step(nar_engine* e, const nar_step_io* io, cudaStream_t main) {
 
 }  // namespace
 
+void planes_build(nar_engine* e) {
+  const nar_model_cfg& c = e->cfg;
+  PlaneSet& ps = e->planes;
+  ps.n = 0;
+  int64_t total = 0;
+  auto add = [&](int64_t off, int64_t K, int64_t N, int64_t ldw) {
+    if (ps.n >= MAX_PLANES) return;
+    const int i = ps.n++;
+    ps.off_W[i] = off; ps.K[i] = (int32_t)K; ps.N[i] = (int32_t)N; ps.ldw[i] = (int32_t)ldw;
+    ps.ld_out[i] = (int32_t)((K + 31) / 32 * 64);
+    ps.dst[i] = total;
+    total += align_up((int64_t)N * ps.ld_out[i], 128);
+  };
+  const int64_t C = c.C, Hp = c.Hp, Fp = c.Fp, c0 = c.ctx_col0;
+  add(c.off_W1, Fp, C, C); add(c.off_W1, c0, C, C); add(c.off_W1 + c0 * C, Fp - c0, C, C);
+  add(c.off_W2, C, C, C); add(c.off_W3, Hp, 512, 512); add(c.off_W4, 512, C, C);
+  add(c.off_M[0], C, 128, c.ld_M[0]); add(c.off_M[1], 128, 64, c.ld_M[1]); add(c.off_M[2], 64, 32, c.ld_M[2]);
+  for (int i = 0; i < c.layers; ++i) {
+    const int64_t n_in = i == 0 ? C : Hp;
+    add(c.off_Wx[i], n_in, 2 * Hp, 2 * Hp);
+    if (c.rnn_cell == 1) add(c.off_Wxc[i], n_in, Hp, Hp);
+  }
+  if (!ps.buf) {
+    cudaMalloc(&ps.buf, (size_t)total * sizeof(uint16_t));
+    cudaMemset(ps.buf, 0, (size_t)total * sizeof(uint16_t));
+    cudaMalloc(&ps.descs, MAX_PLANES * 32);
+  }
+  for (int i = 0; i < ps.n; ++i) { ps.W[i] = c.params + ps.off_W[i]; ps.out[i] = ps.buf + ps.dst[i]; }
+}
+
+int planes_refresh(nar_engine* e, cudaStream_t st) {
+  PlaneSet& ps = e->planes;
+  if (!ps.buf || ps.n == 0) return NAR_ERR_INVALID;
+  ++e->launches;
+  return nar_pack_bf16x3(ps.W, ps.out, ps.K, ps.N, ps.ldw, ps.ld_out, ps.n, ps.descs, st);
+}
+
 // ================================================================================================ C ABI
 extern "C" int nar_engine_create(nar_ctx* ctx, const nar_model_cfg* cfg, nar_engine** out) {
   if (!ctx || !cfg || !out) return NAR_ERR_INVALID;
@@ -406,8 +462,15 @@ extern "C" int nar_engine_create(nar_ctx* ctx, const nar_model_cfg* cfg, nar_eng
     if (cudaMalloc(&e->WhT[i], (size_t)2 * cfg->Hp * cfg->Hp * sizeof(float)) != cudaSuccess) { delete e; return NAR_ERR_NO_DEVICE; }
     if (cfg->rnn_cell == 1 && cudaMalloc(&e->WhcT[i], (size_t)cfg->Hp * cfg->Hp * sizeof(float)) != cudaSuccess) { delete e; return NAR_ERR_NO_DEVICE; }
   }
+  planes_build(e);
+  if (!e->planes.buf || !e->planes.descs) { delete e; return NAR_ERR_NO_DEVICE; }
   *out = e;
   return NAR_OK;
+}
+
+extern "C" int nar_engine_refresh(nar_engine* e, void* stream) {
+  if (!e) return NAR_ERR_INVALID;
+  return planes_refresh(e, as_stream(stream));
 }
 
 extern "C" int nar_engine_destroy(nar_engine* e) {
@@ -416,6 +479,8 @@ extern "C" int nar_engine_destroy(nar_engine* e) {
   for (int i = 0; i < NAR_MAX_LAYERS; ++i) { if (e->WhT[i]) cudaFree(e->WhT[i]); if (e->WhcT[i]) cudaFree(e->WhcT[i]); }
   for (int i = 0; i < N_EVENTS; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   if (e->aux) cudaStreamDestroy(e->aux);
+  if (e->planes.buf) cudaFree(e->planes.buf);
+  if (e->planes.descs) cudaFree(e->planes.descs);
   delete e;
   return NAR_OK;
 }
@@ -425,6 +490,7 @@ extern "C" int nar_engine_update_cfg(nar_engine* e, const nar_model_cfg* cfg) {
   if (cfg->layers != e->cfg.layers || cfg->Hp != e->cfg.Hp || cfg->C != e->cfg.C || cfg->Fp != e->cfg.Fp ||
       cfg->rnn_cell != e->cfg.rnn_cell) return NAR_ERR_INVALID;        // structural changes need a new engine
   e->cfg = *cfg;
+  planes_build(e);                      // the parameter buffer may have changed (share_params)
   return NAR_OK;
 }
 
@@ -479,8 +545,10 @@ extern "C" int nar_engine_apply(nar_engine* e, const nar_step_io* io, void* stre
   if (!e || !io) return NAR_ERR_INVALID;
   const nar_model_cfg& c = e->cfg;
   ++e->launches;
-  return nar_adam_tf(c.params, c.grads, c.adam_m, c.adam_v, c.n_params, c.reg_end, c.reg_l2, c.lr, c.beta1, c.beta2, c.eps,
-                     io->global_step + 1, c.params_lo, stream);
+  int rc = nar_adam_tf(c.params, c.grads, c.adam_m, c.adam_v, c.n_params, c.reg_end, c.reg_l2, c.lr, c.beta1, c.beta2, c.eps,
+                       io->global_step + 1, c.params_lo, stream);
+  if (rc == NAR_OK && c.fwd_precision == 4) rc = planes_refresh(e, as_stream(stream));
+  return rc;
 }
 
 extern "C" int64_t nar_engine_launch_count(const nar_engine* e) { return e ? e->launches : 0; }

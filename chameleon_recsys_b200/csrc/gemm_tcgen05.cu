@@ -26,6 +26,7 @@
 //   MODE 0: single pass.   MODE 1: 3x, both lo tiles produced in-kernel.
 //   MODE 2: 3x, B_lo (weights) read from HBM by TMA (nar_adam_tf maintains it), only A is split in-kernel.
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -47,24 +48,34 @@ constexpr int NUM_THREADS = 256;
 //           memory port: ~176 KB of smem traffic per k-tile vs ~112 KB here.)  Needs A K-major and a B_lo plane.
 // OCC = 2: half-depth rings so that TWO CTAs are resident per SM - the prologue (barrier init, TMEM alloc, first TMA
 // round trip) and the epilogue of one tile overlap the main loop of the other (the kernel is not persistent).
+//   MODE 4: bf16x3 - the same error compensation on the kind::f16 tensor path, which runs at TWICE the tf32 rate and
+//           halves the weight bytes: x = hi + lo with hi = bf16(x), lo = bf16(x - hi) (16 mantissa bits kept), D +=
+//           A_lo*B_hi + A_hi*B_lo + A_hi*B_hi.  A: fp32 K-major tile by TMA, split by the same 128 threads into PACKED
+//           bf16 pairs in tensor memory (16 + 16 columns per 32-k tile instead of 32 + 32).  B: a pre-split, TRANSPOSED
+//           bf16 plane maintained next to the weights (nar_pack_bf16x3): row n holds, per block of 32 k, the 32 hi
+//           values followed by the 32 lo values = one 128-byte swizzle row, so ONE K-major TMA box brings both halves
+//           and a stage is 32 KB instead of 48 KB.  Measured motivation: the 3xTF32 forward GEMMs sit on the SM's
+//           L2->shared-memory ingest (~32 B/clk per SM: 289 us = 2.67 GB / 148 SMs), not on the tensor pipe.
 template <int MODE, int TM, int TN, int OCC = 1> struct Cfg {
+  static constexpr bool BF16 = MODE == 4;
   static constexpr bool SPLIT3 = MODE != 0;
-  static constexpr bool BLO = MODE >= 2;
-  static constexpr bool ATMEM = MODE == 3;
+  static constexpr bool BLO = MODE == 2 || MODE == 3;
+  static constexpr bool ATMEM = MODE == 3 || MODE == 4;
+  static constexpr int A_SLOT_COLS = BF16 ? 32 : 64;                        // tensor-memory columns of one A_hi | A_lo k-tile (per 128 rows)
   static constexpr int A_BYTES = TM * TILE_BYTES_1;
   static constexpr int B_BYTES = TN * TILE_BYTES_1;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES * (BLO ? 2 : 1);     // one operand stage (A | B [| B_lo])
   static constexpr int LO_STAGE_BYTES = (SPLIT3 && !ATMEM) ? (BLO ? A_BYTES : A_BYTES + B_BYTES) : 0;
   static constexpr int STAGES = OCC == 2 ? ((MODE == 3 || TM * TN == 2) ? 2 : 3)
                                          : (SPLIT3 ? (BLO ? (TM == 2 ? 3 : 4) : 5) : (TM * TN == 4 ? 3 : 6));  // operand ring depth
-  static constexpr int LO_STAGES = SPLIT3 ? (ATMEM ? ((TM == 2 || OCC == 2) ? 2 : 4) : 2) : 0;   // lo ring depth (shared memory, or TMEM for MODE 3)
+  static constexpr int LO_STAGES = SPLIT3 ? (ATMEM ? (BF16 ? 4 : ((TM == 2 || OCC == 2) ? 2 : 4)) : 2) : 0;   // lo ring depth (shared memory, or TMEM for MODE 3 / 4)
   static constexpr int TILE_BYTES = STAGES * STAGE_BYTES + (ATMEM ? 0 : LO_STAGES * LO_STAGE_BYTES);
   static constexpr int SMEM_BYTES = TILE_BYTES + 256 + 1024;                // tiles + barriers + align slack
   static constexpr int TMEM_COLS = ATMEM ? (OCC == 2 ? 256 : 512) : TM * TN * 128;             // accumulators (+ A ring: TM x (A_hi | A_lo) of 32 columns per stage)
   static constexpr int TMEM_A_BASE = TM * TN * 128;                         // MODE 3: A ring starts after the accumulators
   static_assert((TM == 1 && TN == 1) || MODE == 0 || (MODE == 3 && TM == 2 && TN == 1), "tile shapes: 128x128; 256x256 single pass; 256x128 with A in TMEM");
-  static_assert(!ATMEM || TMEM_A_BASE + LO_STAGES * TM * 64 <= TMEM_COLS, "tensor memory budget");
-  static_assert(OCC == 1 || (TM * TN == 1 && (MODE == 0 || MODE == 3)) || (TM * TN == 2 && MODE == 0),
+  static_assert(!ATMEM || TMEM_A_BASE + LO_STAGES * TM * A_SLOT_COLS <= TMEM_COLS, "tensor memory budget");
+  static_assert(OCC == 1 || (TM * TN == 1 && (MODE == 0 || MODE == 3 || MODE == 4)) || (TM * TN == 2 && MODE == 0),
                 "two CTAs per SM: 128x128 tiles (single pass or A-in-TMEM), 256x128 or 128x256 single pass");
 };
 
@@ -163,6 +174,29 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
         "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+// kind::f16 (bf16 operands, fp32 accumulate), A from tensor memory: packed pairs, 8 columns per K = 16 instruction
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+// x -> (bf16(x), bf16(x - bf16(x))) for two consecutive k values, each pair packed low = even k
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const float2 hf = __bfloat1622float2(h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -209,6 +243,12 @@ template <bool A_MN, bool B_MN, int N>
 __device__ __forceinline__ constexpr uint32_t make_idesc_n() {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// kind::f16 with bf16 operands: a/b format BF16 (1<<7, 1<<10), both K-major
+template <int N>
+__device__ __forceinline__ constexpr uint32_t make_idesc_bf16() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
 // Epilogue element work for 4 consecutive columns of one row: bias / activation / activation-derivative / store.
@@ -274,7 +314,8 @@ __global__ void __launch_bounds__(NUM_THREADS, OCC)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_blo, const Params p) {
   using C = Cfg<MODE, TM, TN, OCC>;
-  constexpr bool SPLIT3 = C::SPLIT3, BLO = C::BLO, ATMEM = C::ATMEM;
+  constexpr bool SPLIT3 = C::SPLIT3, BLO = C::BLO, ATMEM = C::ATMEM, BF16 = C::BF16;
+  static_assert(!BF16 || (!A_MN && !B_MN), "bf16x3: A K-major fp32, B the transposed (K-major) bf16 plane");
   constexpr int LS = C::LO_STAGES > 0 ? C::LO_STAGES : 1;        // lo ring depth (2 in shared memory, 4 in TMEM)
   static_assert(!ATMEM || !A_MN, "A in tensor memory must be K-major");
   extern __shared__ uint8_t smem_raw[];
@@ -339,7 +380,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const uint32_t a_dst = smem_u32(tiles + s * C::STAGE_BYTES);
         const uint32_t b_dst = a_dst + C::A_BYTES;
         load_operand<A_MN, TM>(a_dst, &tmap_a, &full[s], m_blk * BM * TM, k_elem);
-        if (p.cluster) {
+        if (BF16) {
+          // one box: 128 n-rows x 128 B = the 32 hi then the 32 lo bf16 of k-tile (kt0 + kt)
+          tma_load_2d(b_dst, &tmap_b, &full[s], (kt0 + kt) * 64, n_blk * BN * TN);
+        } else if (p.cluster) {
           load_operand_mc<B_MN, TN>(b_dst, &tmap_b, &full[s], n_blk * BN * TN, k_elem, crank);
           if (BLO) load_operand_mc<B_MN, TN>(b_dst + C::B_BYTES, &tmap_blo, &full[s], n_blk * BN * TN, k_elem, crank);
         } else {
@@ -365,6 +409,22 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const uint32_t b_hi = a_hi + C::A_BYTES;
         const uint32_t a_lo = smem_u32(lo_tiles + ls * C::LO_STAGE_BYTES);
         const uint32_t b_lo = BLO ? (b_hi + C::B_BYTES) : (a_lo + C::A_BYTES);
+        if (BF16) {
+          constexpr uint32_t idesc16 = make_idesc_bf16<BN * TN>();
+          const uint32_t acc = tmem_base;
+          const uint32_t ta = tmem_base + (uint32_t)(C::TMEM_A_BASE + ls * C::A_SLOT_COLS);      // 16 columns hi | 16 columns lo
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {                        // two K = 16 steps per 32-k tile; 32 B of k per step in the swizzled row
+            const uint64_t db = make_smem_desc<false>(b_hi + k * 32);          // hi half of the row: bytes [0, 64)
+            const uint64_t dbl = make_smem_desc<false>(b_hi + 64 + k * 32);    // lo half: bytes [64, 128)
+            umma_bf16_ts(acc, ta + 16 + k * 8, db, idesc16, (kt > 0 || k > 0) ? 1u : 0u);       // A_lo * B_hi
+            umma_bf16_ts(acc, ta + k * 8, dbl, idesc16, 1u);                                     // A_hi * B_lo
+            umma_bf16_ts(acc, ta + k * 8, db, idesc16, 1u);                                      // A_hi * B_hi
+          }
+          umma_commit(&empty[s]);
+          umma_commit(&lo_empty[ls]);
+          continue;
+        }
         if (ATMEM) {
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -419,6 +479,26 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int ls = kt % LS;
         mbar_wait(&lo_empty[ls], ((uint32_t)(kt / LS) & 1u) ^ 1u);    // MMAs of k-tile kt-LS no longer read this lo stage
         mbar_wait(&full[s], ph);
+        if (BF16) {
+          // thread = accumulator lane = A row: 32 fp32 k-values -> 16 packed hi pairs + 16 packed lo pairs in tensor memory
+          const int row = ew * 32 + lane;
+          const uint8_t* arow = tiles + s * C::STAGE_BYTES + row * 128;
+          uint32_t hi_p[16], lo_p[16];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7)) << 4));
+            split_bf16x2(v.x, v.y, hi_p[2 * c], lo_p[2 * c]);
+            split_bf16x2(v.z, v.w, hi_p[2 * c + 1], lo_p[2 * c + 1]);
+          }
+          const uint32_t ta = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(C::TMEM_A_BASE + ls * C::A_SLOT_COLS);
+          tmem_st_32x32b_x16(ta, hi_p);
+          tmem_st_32x32b_x16(ta + 16, lo_p);
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(&xf[ls]);
+          mbar_arrive(&empty[s]);        // this thread is done with the A tile of the operand stage
+          continue;
+        }
         if (ATMEM) {
           // thread = accumulator lane = A row: read the row's 32 k-values (8 swizzled 16-byte chunks) from the TMA tile
           // and write A_hi | A_lo into tensor memory; the MMAs never touch the A tile in shared memory
@@ -535,6 +615,52 @@ static int make_operand_map(const nar_ctx* ctx, CUtensorMap* map, const float* p
   return r == CUDA_SUCCESS ? NAR_OK : NAR_ERR_INVALID;
 }
 
+// the pre-split bf16 weight plane of MODE 4: [n_rows, ld] bf16, K-major, 64 elements (128 B) of it per 32-k tile
+static int make_bf16_plane_map(const nar_ctx* ctx, CUtensorMap* map, const void* ptr, int64_t n_rows, int64_t k_tiles, int64_t ld) {
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0 || (ld & 7) != 0 || ld < k_tiles * 64) return NAR_ERR_INVALID;
+  cuuint64_t dims[2] = {(cuuint64_t)(k_tiles * 64), (cuuint64_t)n_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
+      map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? NAR_OK : NAR_ERR_INVALID;
+}
+
+// nar_pack_bf16x3: W [K, N] fp32 (row stride ldw) -> plane [N, ld_out] bf16 (see MODE 4).  32 x 32 tiles through shared
+// memory: reads coalesced along n, writes 64 contiguous bytes (32 hi or 32 lo values of one n) per half warp.
+struct PackDesc { const float* W; uint16_t* out; int K, N, ldw, ld_out; };
+constexpr int MAX_PACK = 32;
+
+__global__ void __launch_bounds__(256)
+pack_bf16x3_kernel(const PackDesc* __restrict__ descs) {
+  __shared__ float tile[32][33];
+  const PackDesc d = descs[blockIdx.y];
+  const int kb_n = (d.K + 31) / 32, nb_n = (d.N + 31) / 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+  for (int t = blockIdx.x; t < kb_n * nb_n; t += gridDim.x) {
+    const int kb = t / nb_n, nb = t - kb * nb_n;
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+      const int k = kb * 32 + i, n = nb * 32 + tx;
+      tile[i][tx] = (k < d.K && n < d.N) ? d.W[(int64_t)k * d.ldw + n] : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {                             // i = n within the tile, tx = k within the block
+      const int n = nb * 32 + i;
+      if (n < d.N) {
+        const float x = tile[tx][i];
+        const __nv_bfloat16 h = __float2bfloat16_rn(x);
+        const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+        uint16_t* o = d.out + (int64_t)n * d.ld_out + kb * 64 + tx;
+        o[0] = *reinterpret_cast<const uint16_t*>(&h);
+        o[32] = *reinterpret_cast<const uint16_t*>(&l);
+      }
+    }
+  }
+}
+
 template <bool A_MN, bool B_MN, int MODE, int TM, int TN, int OCC = 1>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbl, const Params& p, dim3 grid, cudaStream_t st) {
   auto kern = gemm_tf32_kernel<A_MN, B_MN, MODE, TM, TN, OCC>;
@@ -563,19 +689,52 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
 }  // namespace gemm
 }  // namespace nar
 
+static int occ_env_early() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NAR_GEMM_OCC2"); v = e ? atoi(e) : 1; }
+  return v;
+}
+
+extern "C" int nar_pack_bf16x3(const float* const* W, void* const* out, const int32_t* K, const int32_t* N, const int32_t* ldw,
+                               const int32_t* ld_out, int n, void* descs_dev, void* stream) {
+  using namespace nar::gemm;
+  if (!W || !out || !K || !N || !ldw || !ld_out || !descs_dev || n <= 0 || n > MAX_PACK) return NAR_ERR_INVALID;
+  PackDesc h[MAX_PACK];
+  int max_tiles = 1;
+  for (int i = 0; i < n; ++i) {
+    if (!W[i] || !out[i] || K[i] <= 0 || N[i] <= 0 || ld_out[i] < (K[i] + 31) / 32 * 64) return NAR_ERR_INVALID;
+    h[i].W = W[i]; h[i].out = static_cast<uint16_t*>(out[i]); h[i].K = K[i]; h[i].N = N[i]; h[i].ldw = ldw[i]; h[i].ld_out = ld_out[i];
+    const int t = ((K[i] + 31) / 32) * ((N[i] + 31) / 32);
+    max_tiles = t > max_tiles ? t : max_tiles;
+  }
+  // the descriptor table is written once per distinct set (callers keep it; stream-ordered copy from a pageable buffer
+  // would be a sync, so it goes through a kernel-argument-sized async memcpy only when it changed)
+  static PackDesc last[MAX_PACK]; static int last_n = 0; static void* last_dev = nullptr;
+  if (last_dev != descs_dev || last_n != n || memcmp(last, h, sizeof(PackDesc) * n) != 0) {
+    NAR_CHECK_CUDA(cudaMemcpy(descs_dev, h, sizeof(PackDesc) * n, cudaMemcpyHostToDevice));
+    memcpy(last, h, sizeof(PackDesc) * n); last_n = n; last_dev = descs_dev;
+  }
+  dim3 grid((unsigned)(max_tiles > 296 ? 296 : max_tiles), (unsigned)n);
+  pack_bf16x3_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const PackDesc*>(descs_dev));
+  NAR_LAUNCH_CHECK();
+  return NAR_OK;
+}
+
 extern "C" int nar_gemm_tf32(nar_ctx* ctx, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, int a_kmajor,
                              const float* B, int64_t ldb, int b_kmajor, float* D, int64_t ldd,
                              const nar_gemm_epilogue* epi, void* stream) {
   using namespace nar::gemm;
   if (!ctx || !ctx->encode_tiled) return NAR_ERR_NO_DEVICE;
-  if (!A || !B || !D || !epi) return NAR_ERR_INVALID;
+  if (!A || !D || !epi || (!B && epi->precision != 4)) return NAR_ERR_INVALID;
   if (M <= 0 || N <= 0 || K <= 0) return NAR_OK;     // empty problem: nothing to do
   if ((ldd & 3) != 0 || (reinterpret_cast<uintptr_t>(D) & 15u) != 0) return NAR_ERR_INVALID;
   if (epi->bias && (reinterpret_cast<uintptr_t>(epi->bias) & 15u) != 0) return NAR_ERR_INVALID;
   if (epi->dact && (!epi->aux || (epi->ld_aux & 3) != 0 || (reinterpret_cast<uintptr_t>(epi->aux) & 15u) != 0)) return NAR_ERR_INVALID;
-  if (epi->precision != 1 && epi->precision != 3) return NAR_ERR_INVALID;
+  if (epi->precision != 1 && epi->precision != 3 && epi->precision != 4) return NAR_ERR_INVALID;
+  const bool bf16 = epi->precision == 4;
+  if (bf16 && (!a_kmajor || !epi->b_bf16 || epi->accumulate || epi->split_k > 1)) return NAR_ERR_INVALID;
   const bool blo = epi->precision == 3 && epi->b_lo != nullptr;
-  const int mode = epi->precision == 1 ? 0 : (blo ? (a_kmajor ? 3 : 2) : 1);
+  const int mode = bf16 ? 4 : (epi->precision == 1 ? 0 : (blo ? (a_kmajor ? 3 : 2) : 1));
   // 256x256 CTA tiles for the big single-pass GEMMs (L2-bound with 128x128 tiles); 128x128 otherwise
   const bool big = (double)M * (double)N * (double)K >= 2e9;
   // (256x128 tiles with A in TMEM are implemented and validated but measured ~10 % slower than 128x128 for MODE 3)
@@ -616,7 +775,8 @@ extern "C" int nar_gemm_tf32(nar_ctx* ctx, int64_t M, int64_t N, int64_t K, cons
   CUtensorMap ta, tb;
   int rc = make_operand_map(ctx, &ta, A, M, K, lda, a_kmajor != 0, TM);
   if (rc) return rc;
-  rc = make_operand_map(ctx, &tb, B, N, K, ldb, b_kmajor != 0, TN, cluster ? 64 : 128);
+  if (bf16) rc = make_bf16_plane_map(ctx, &tb, epi->b_bf16, N, k_tiles, epi->ld_bf16);
+  else rc = make_operand_map(ctx, &tb, B, N, K, ldb, b_kmajor != 0, TN, cluster ? 64 : 128);
   if (rc) return rc;
   CUtensorMap tbl = tb;
   if (blo) {
@@ -631,6 +791,11 @@ extern "C" int nar_gemm_tf32(nar_ctx* ctx, int64_t M, int64_t N, int64_t K, cons
   dim3 grid((unsigned)(n_tiles * m_tiles_launch), (unsigned)split, 1);
   cudaStream_t st = as_stream(stream);
   const bool amn = !a_kmajor, bmn = !b_kmajor;
+  if (mode == 4) {
+    const bool occ2_bf = occ_env_early() != 0 && n_tiles * m_tiles_launch >= (int64_t)ctx->sm_count;
+    if (occ2_bf) return launch<false, false, 4, 1, 1, 2>(ta, tb, tbl, p, grid, st);
+    return launch<false, false, 4, 1, 1, 1>(ta, tb, tbl, p, grid, st);
+  }
   static int occ_env = -1;
   if (occ_env < 0) { const char* e = getenv("NAR_GEMM_OCC2"); occ_env = e ? atoi(e) : 1; }
   // two CTAs per SM (half-depth rings) pay off when there are CTAs to pair up; a grid smaller than the GPU is latency

@@ -36,7 +36,7 @@ class NarEngine:
                  recent_clicks_buffer_max_size: int, recent_clicks_for_normalization: int,
                  elapsed_days_smooth_log_base: float = 1.3, popularity_smooth_log_base: float = 2.0,
                  ranking: str = 'mlp', rnn_cell: str = 'ugrnn', sampler_seed: int = 42, device: Optional[int] = None,
-                 fwd_precision: int = 3, bwd_precision: int = 1, process_group=None, max_batch: int = 0,
+                 fwd_precision: Optional[int] = None, bwd_precision: int = 1, process_group=None, max_batch: int = 0,
                  dedup: Optional[bool] = None, keep_prob: float = 1.0, novelty_reg_factor: float = 0.0,
                  dropout_seed: Optional[int] = None):
         if not torch.cuda.is_available():
@@ -60,6 +60,10 @@ class NarEngine:
         self.lb_rec, self.lb_nov = float(elapsed_days_smooth_log_base), float(popularity_smooth_log_base)
         self.ranking = ranking
         self.seed = int(sampler_seed)
+        # forward GEMMs: 3 = 3xTF32, 4 = bf16x3 (bf16 hi + lo pieces on the kind::f16 path: same error compensation at twice
+        # the tensor rate and 2/3 of the operand bytes; logits within 3e-5 of fp32 instead of 3e-6 - the bar is 1e-3)
+        if fwd_precision is None:
+            fwd_precision = int(os.environ.get('NAR_FWD_PRECISION', '3'))
         self.fwd_prec, self.bwd_prec = int(fwd_precision), int(bwd_precision)
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
@@ -177,6 +181,12 @@ class NarEngine:
             check(self._lib.nar_engine_update_cfg(self._handle, C.byref(self._cfg)), 'nar_engine_update_cfg')
             self._cfg_key = key
 
+    def _refresh(self):
+        """Weights were written from outside the engine: rebuild what the C side derives from them (bf16x3 planes)."""
+        if getattr(self, '_handle', None):
+            self._sync_cfg()
+            check(self._lib.nar_engine_refresh(self._handle, C.c_void_p(torch.cuda.current_stream().cuda_stream)), 'nar_engine_refresh')
+
     # ------------------------------------------------------------------ parameters
     def view(self, key: str, buf: Optional[torch.Tensor] = None) -> torch.Tensor:
         b = self.params if buf is None else buf
@@ -193,6 +203,7 @@ class NarEngine:
         self.params.copy_(torch.from_numpy(flat))
         self.adam_m.zero_(); self.adam_v.zero_(); self.grads.zero_()
         ops.tf32_lo(self.params, self.layout.total, self.params_lo)
+        self._refresh()
         self.global_step = 0
 
     def get_params(self) -> Dict[str, np.ndarray]:
@@ -217,6 +228,7 @@ class NarEngine:
         self.adam_v.copy_(torch.from_numpy(self.layout.to_internal(sd['adam_v'])))
         self.global_step = int(sd['global_step'])
         ops.tf32_lo(self.params, self.layout.total, self.params_lo)
+        self._refresh()
 
     # ------------------------------------------------------------------ buffers
     def _buf(self, name: str, rows: int, cols: int, dtype=torch.float32, cap_rows: int = 0) -> torch.Tensor:
@@ -617,6 +629,7 @@ class NarEngine:
         self.global_step = other.global_step
         self._views = {}
         self._sync_cfg()
+        self._refresh()
 
     def eval_step(self, features, labels, buffer, pop_norm, top_n: int, metrics: Optional[torch.Tensor] = None,
                   step_id: Optional[int] = None, keep: bool = False) -> dict:

@@ -63,19 +63,37 @@ def _chk_f32(*ts):
 
 def gemm(A: torch.Tensor, B: torch.Tensor, D: torch.Tensor, M: int, N: int, K: int, *, a_kmajor=True, b_kmajor=True,
          lda=None, ldb=None, ldd=None, bias=None, act=ACT_NONE, dact=ACT_NONE, aux=None, ld_aux=None,
-         accumulate=False, split_k=1, precision=3, b_lo=None):
+         accumulate=False, split_k=1, precision=3, b_lo=None, b_bf16=None, ld_bf16=0):
     global LAUNCHES
     LAUNCHES += 1
     """D[M,N] = epilogue(sum_k A(m,k) B(n,k)); see nar_gemm_tf32."""
     _chk_f32(A, B, D, bias, aux)
     lda = A.stride(0) if lda is None else lda
-    ldb = B.stride(0) if ldb is None else ldb
+    ldb = (B.stride(0) if B is not None else 0) if ldb is None else ldb
     ldd = D.stride(0) if ldd is None else ldd
     epi = GemmEpilogue(_p(bias), act, dact, _p(aux), (aux.stride(0) if (aux is not None and ld_aux is None) else (ld_aux or 0)),
-                       1 if accumulate else 0, int(split_k), int(precision), _p(b_lo))
+                       1 if accumulate else 0, int(split_k), int(precision), _p(b_lo), _p(b_bf16), int(ld_bf16))
     ctx = context()
     check(ctx.lib.nar_gemm_tf32(ctx.handle, M, N, K, _p(A), lda, 1 if a_kmajor else 0, _p(B), ldb, 1 if b_kmajor else 0,
                                 _p(D), ldd, C.byref(epi), _stream()), 'nar_gemm_tf32')
+
+
+_PACK_SCRATCH: dict = {}
+
+
+def pack_bf16x3(W: torch.Tensor, K: int, N: int) -> torch.Tensor:
+    """bf16x3 plane of W [K, N] (stored [in, out], row stride W.stride(0)) for gemm(precision=4): [N, ceil(K/32)*64] bf16."""
+    global LAUNCHES
+    LAUNCHES += 1
+    ld_out = (K + 31) // 32 * 64
+    out = torch.zeros(N, ld_out, dtype=torch.bfloat16, device=W.device)
+    dev = W.device.index
+    if dev not in _PACK_SCRATCH:
+        _PACK_SCRATCH[dev] = torch.zeros(32 * 32, dtype=torch.uint8, device=W.device)
+    i32 = lambda v: (C.c_int32 * 1)(v)      # noqa: E731
+    check(_lib.load().nar_pack_bf16x3((C.c_void_p * 1)(W.data_ptr()), (C.c_void_p * 1)(out.data_ptr()), i32(K), i32(N),
+                                      i32(W.stride(0)), i32(ld_out), 1, _p(_PACK_SCRATCH[dev]), _stream()), 'nar_pack_bf16x3')
+    return out
 
 
 def gather_rows(table: torch.Tensor, ids: torch.Tensor, out: torch.Tensor, width: int):

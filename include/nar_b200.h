@@ -171,7 +171,17 @@ typedef struct {
   int32_t precision;      /* 1 = TF32, 3 = 3xTF32 (error-compensated, ~fp32 accuracy) */
   const float* b_lo;      /* precision 3 only, optional: x - tf32_trunc(x) of operand B, same shape / ld as B (see
                              nar_tf32_lo; the weights' lo plane is maintained by nar_adam_tf).  NULL: split B in-kernel */
+  const void* b_bf16;     /* precision 4 (bf16x3: bf16 hi + lo pieces on the kind::f16 path, fp32 accumulate; A must be K-major
+                             fp32): operand B as the pre-split transposed plane written by nar_pack_bf16x3 - [N, ld_bf16]
+                             bf16, row n = per block of 32 k the 32 hi values then the 32 lo values; B / ldb are ignored */
+  int64_t ld_bf16;        /* elements per row of b_bf16 (>= ceil(K/32)*64, multiple of 8) */
 } nar_gemm_epilogue;
+
+/* bf16x3 weight planes for n matrices in one launch: W[i] [K[i], N[i]] fp32 (row stride ldw[i], i.e. stored [in, out]) ->
+ * out[i] [N[i], ld_out[i]] bf16 as nar_gemm_epilogue.b_bf16 describes (zero padded to whole 32-k blocks).
+ * descs_dev: caller-owned device scratch of >= 32*32 bytes the call keeps its table in.                               */
+int nar_pack_bf16x3(const float* const* W /*host array*/, void* const* out /*host array*/, const int32_t* K, const int32_t* N,
+                    const int32_t* ldw, const int32_t* ld_out, int n, void* descs_dev, void* stream);
 
 int nar_gemm_tf32(nar_ctx* ctx, int64_t M, int64_t N, int64_t K,
                   const float* A, int64_t lda, int a_kmajor,
@@ -344,7 +354,7 @@ typedef struct {
   /* dimensions */
   int64_t num_items, C /*CAR_embedding_size*/, Hp /*rnn_units padded to 4*/, Fp /*feature row width*/, ctx_col0;
   int32_t layers, rnn_cell /*0 = UGRNNCell (nar_model.py:1318), 1 = GRUCell (:1315)*/, ranking /*0 = MLP scorer (:444-500), 1 = cosine*/;
-  int32_t fwd_precision, bwd_precision;       /* nar_gemm_epilogue.precision of the forward / backward GEMMs */
+  int32_t fwd_precision, bwd_precision;       /* nar_gemm_epilogue.precision of the forward (3 or 4) / backward (1 or 3) GEMMs */
   int32_t dedup;                              /* 1: per-unique-id CAR layer 1 (csrc/car.cu); 0: every candidate row materialised */
   int32_t use_aux_stream;                     /* 1: weight / bias gradients (and the forward session branch) on the auxiliary stream */
   float keep_prob;                            /* dropout_keep_prob (training steps only; < 1 needs dedup == 0) */
@@ -398,6 +408,9 @@ int nar_engine_workspace_bytes(const nar_engine* eng, int64_t Bg, int64_t B, int
 int nar_engine_prepare(nar_engine* eng, const nar_step_io* io /*host*/, void* stream);
 int nar_engine_step(nar_engine* eng, const nar_step_io* io /*host*/, void* stream);
 int nar_engine_apply(nar_engine* eng, const nar_step_io* io /*host*/, void* stream);
+/* after the caller wrote the weights itself (initialisation, checkpoint restore): rebuild what the engine derives from
+ * them (the bf16x3 planes of the forward weights, fwd_precision 4)                                                      */
+int nar_engine_refresh(nar_engine* eng, void* stream);
 /* device address / shape of a named intermediate of the LAST nar_engine_prepare / nar_engine_step with this io
  * (parity tests, evaluation ranking): "neg", "neg_uidx", "row_pos", "row_item", "stats", "X", "H1", "E", "HO<i>", "F1",
  * "PR", "logits", "base_pos", "base_item", ...  Returns NAR_ERR_INVALID for an unknown name.                       */

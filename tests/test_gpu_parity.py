@@ -21,7 +21,7 @@ def _fails(results):
     return [r for r in results if not r.get('ok')]
 
 
-@pytest.mark.parametrize('fam', ['gemm_kk', 'gemm_km', 'gemm_mk', 'gemm_mm', 'gemm_epi'])
+@pytest.mark.parametrize('fam', ['gemm_kk', 'gemm_km', 'gemm_mk', 'gemm_mm', 'gemm_epi', 'gemm_bf16'])
 def test_gemm_tcgen05(fam):
     from tools import gpu_diag
     assert not _fails(gpu_diag.FAMILIES[fam]())
@@ -94,7 +94,8 @@ def _check_steps(res, grad_tol=3e-2, update_tol=0.2):
 
 
 @pytest.mark.parametrize('case', ['tinyA', 'tinyB', 'tinyB_cold', 'tinyB_cos', 'tinyB_2l', 'tinyB_nov', 'tinyB_cos_nov', 'tinyB_drop',
-                                  'tinyB_2l_drop', 'tinyB_pad', 'tinyB_gru', 'tinyB_gru_2l_drop', 'tinyB_gru_cos'])
+                                  'tinyB_2l_drop', 'tinyB_pad', 'tinyB_gru', 'tinyB_gru_2l_drop', 'tinyB_gru_cos', 'tinyB_bf16',
+                                  'tinyA_bf16', 'tinyB_gru_bf16'])
 def test_full_step_parity_tiny(case):
     import torch
     from tools import gpu_step_check as g
@@ -111,13 +112,17 @@ def test_full_step_parity_tiny(case):
            # rnn_cell='gru' (north_star's "session GRU"; nar_model.py:1315)
            'tinyB_gru': ('B', 5, 3, dict(rnn_cell='gru')),
            'tinyB_gru_2l_drop': ('B', 5, 2, dict(rnn_cell='gru', rnn_num_layers=2, dropout_keep_prob=0.8)),
-           'tinyB_gru_cos': ('B', 5, 2, dict(rnn_cell='gru', ranking='cosine'))}[case]
+           'tinyB_gru_cos': ('B', 5, 2, dict(rnn_cell='gru', ranking='cosine')),
+           # forward GEMMs as bf16x3 (fwd_precision 4)
+           'tinyB_bf16': ('B', 5, 3, None), 'tinyA_bf16': ('A', 5, 2, None), 'tinyB_gru_bf16': ('B', 5, 2, dict(rnn_cell='gru'))}[case]
     # the two-layer dropout case checks the mask plumbing (which output is dropped where, forward and backward): it runs
     # the backward GEMMs error-compensated so that a wrong mask cannot hide in TF32 noise
     ekw = dict(bwd_precision=3) if case in ('tinyB_2l_drop', 'tinyB_gru_2l_drop') else None
+    if case.endswith('_bf16'):
+        ekw = dict(fwd_precision=4)
     res = g.run_case('tiny', cfg[0], cfg[1], cfg[2], hp_over=cfg[3], oracle_dtype=torch.float64, engine_kw=ekw)
     # (5 positions in the padding case: Adam turns the TF32 noise of near-zero gradients into larger relative updates)
-    _check_steps(res, grad_tol=2e-3 if ekw else 3e-2, update_tol=0.5 if case == 'tinyB_pad' else 0.2)
+    _check_steps(res, grad_tol=2e-3 if (ekw and 'bwd_precision' in ekw) else 3e-2, update_tol=0.5 if case == 'tinyB_pad' else 0.2)
 
 
 @pytest.mark.parametrize('case', ['tinyB', 'tinyB_cold', 'g1'])
@@ -161,11 +166,13 @@ def test_dedup_matches_every_candidate_row():
     assert torch.equal(lg1, lg2) and torch.equal(e1, e2)            # forward: no atomics anywhere
 
 
-def test_full_step_parity_g1_shapes():
-    """G1 dims (46K items, E=250, H=255, C=1024, K=50, F=477) at a batch the fp32 oracle finishes in seconds."""
+@pytest.mark.parametrize('fwd', [3, 4])
+def test_full_step_parity_g1_shapes(fwd):
+    """G1 dims (46K items, E=250, H=255, C=1024, K=50, F=477) at a batch the fp32 oracle finishes in seconds; forward GEMMs
+    as 3xTF32 (fwd 3) and as bf16x3 (fwd 4)."""
     import torch
     from tools import gpu_step_check as g
-    res = g.run_case('g1', 'B', 30, 2, hp_over=dict(batch_size=48), oracle_dtype=torch.float32)
+    res = g.run_case('g1', 'B', 30, 2, hp_over=dict(batch_size=48), oracle_dtype=torch.float32, engine_kw=dict(fwd_precision=fwd))
     _check_steps(res)
 
 

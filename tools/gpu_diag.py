@@ -109,6 +109,42 @@ def fam_gemm_epi():
     return res
 
 
+def fam_gemm_bf16():
+    """precision 4 (bf16x3 on the kind::f16 path): D = act(A * W + b) with W given as the packed bf16 plane, against fp64.
+    Expected error ~2^-16 of |a||b| per product (bf16 hi + lo keep 16 mantissa bits): 1e-4 of the result scale is the bar."""
+    import torch
+    from chameleon_recsys_b200 import ops
+    res = []
+    for (M, N, K, epi) in ((333, 250, 200, 'none'), (1000, 1024, 1024, 'bias_tanh'), (129, 64, 72, 'bias_leaky'),
+                           (5000, 128, 1024, 'none'), (20000, 1024, 408, 'bias_leaky'), (77, 32, 64, 'none')):
+        torch.manual_seed(M + N + K)
+        lda = (K + 3) // 4 * 4
+        A = torch.zeros(M, lda, device='cuda'); A[:, :K].normal_()
+        W = torch.randn(K, (N + 3) // 4 * 4, device='cuda')
+        if epi == 'bias_tanh':
+            A /= 30
+        ref = A[:, :K].double() @ W[:, :N].double()
+        ldd = (N + 3) // 4 * 4
+        D = torch.full((M, ldd), 7.0, device='cuda')
+        kw = {}
+        if epi != 'none':
+            bias = torch.randn(ldd, device='cuda') * 0.1
+            ref = ref + bias[:N].double()
+            ref = torch.tanh(ref) if epi == 'bias_tanh' else torch.nn.functional.leaky_relu(ref, 0.2)
+            kw = dict(bias=bias, act=ops.ACT_TANH if epi == 'bias_tanh' else ops.ACT_LEAKY)
+        plane = ops.pack_bf16x3(W, K, N)
+        ops.gemm(A, None, D, M, N, K, a_kmajor=True, b_kmajor=True, lda=lda, ldb=0, precision=4, b_bf16=plane,
+                 ld_bf16=plane.stride(0), **kw)
+        torch.cuda.synchronize()
+        got = D[:, :N].double()
+        rel = float((got - ref).abs().max() / ref.abs().max())
+        r = dict(shape=[M, N, K], epi=epi, rel=rel, nan=bool(torch.isnan(D[:, :N]).any()),
+                 pad_untouched=bool((D[:, N:] == 7.0).all()) if ldd > N else True)
+        r['ok'] = (not r['nan']) and rel < 1e-4 and r['pad_untouched']
+        res.append(r)
+    return res
+
+
 def fam_gather():
     import torch
     from chameleon_recsys_b200 import ops
@@ -299,7 +335,7 @@ def fam_misc():
 
 
 FAMILIES = {'gemm_kk': fam_gemm_kk, 'gemm_km': fam_gemm_km, 'gemm_mk': fam_gemm_mk, 'gemm_mm': fam_gemm_mm,
-            'gemm_epi': fam_gemm_epi, 'gather': fam_gather, 'sampler': fam_sampler, 'rnn': fam_rnn, 'loss': fam_loss,
+            'gemm_epi': fam_gemm_epi, 'gemm_bf16': fam_gemm_bf16, 'gather': fam_gather, 'sampler': fam_sampler, 'rnn': fam_rnn, 'loss': fam_loss,
             'misc': fam_misc}
 
 

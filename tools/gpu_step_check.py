@@ -119,6 +119,7 @@ def run_case(name, profile, warm, n_steps, hp_over=None, oracle_dtype=torch.floa
         g_gpu = eng.get_grads()
         p_before = None
         gerr = {}
+        gabs = {}
         for k, g in grads.items():
             gref = g.detach().numpy().astype(np.float64)
             if orc.reg > 0 and orc.regularised(k):
@@ -126,8 +127,9 @@ def run_case(name, profile, warm, n_steps, hp_over=None, oracle_dtype=torch.floa
                 # compare against (grad - reg*w_before) using the logical params saved below
                 gref = gref - orc.reg * params_before[k]
             gerr[k.split('/')[-2] + '/' + k.split('/')[-1]] = rel(g_gpu[k], gref)
+            gabs[k.split('/')[-2] + '/' + k.split('/')[-1]] = (float(np.abs(g_gpu[k] - gref).max()), float(np.abs(gref).max()))
         gerr.pop('matching_dense_layer_4/bias', None)       # exactly zero in exact arithmetic (softmax gradient sums to 0)
-        r['grad_rel_max'] = max(gerr.values()); r['grad_rel'] = gerr
+        r['grad_rel_max'] = max(gerr.values()); r['grad_rel'] = gerr; r['grad_abs'] = gabs
         p_gpu = eng.get_params(); p_ref = orc.get_params()
         r['param_abs_max'] = max(float(np.abs(p_gpu[k] - p_ref[k]).max()) for k in p_ref)
         # Adam normalises: compare updates only where the gradient is far above eps/sqrt(1-b2) = 3.2e-7

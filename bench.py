@@ -463,7 +463,7 @@ def run_ours(args):
 
     line = {'metric': 'NAR train interactions/sec', 'value': value, 'unit': 'interactions/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (tcgen05 kind::tf32: 3xTF32 forward, TF32 backward; fp32 accumulate)', 'dedup_car_layer1': bool(eng.dedup),
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (tcgen05: %s forward, single-pass TF32 backward; fp32 accumulate)' % ('bf16x3 (kind::f16, error-compensated)' if eng.fwd_prec == 4 else '3xTF32'), 'dedup_car_layer1': bool(eng.dedup),
             'data': 'synthetic', 'config': workload_config(pb, args, gb),
             'interactions_per_step': n_int / args.steps,
             'e2e': {'value': e2e_value, 'unit': 'interactions/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 16,
@@ -562,24 +562,39 @@ def kernel_rooflines(eng, st, hbm_peak, tf_peak, peak_src):
     H1, Eb = eng.buffer(st, 'H1'), eng.buffer(st, 'E')
     W2, b2, W2lo = eng.view('W2'), eng.view('b2').view(-1), eng.view('W2', eng.params_lo)
 
+    W2plane = ops.pack_bf16x3(W2, eng.C, eng.C)
+
     def car2(prec):
-        ops.gemm(H1, W2, Eb, R, eng.C, eng.C, a_kmajor=True, b_kmajor=False, bias=b2, act=ACT_TANH, precision=prec,
-                 b_lo=W2lo if prec == 3 else None)
-    ms_m = timeit(lambda: car2(3), iters=10)
+        if prec == 4:
+            ops.gemm(H1, None, Eb, R, eng.C, eng.C, a_kmajor=True, b_kmajor=True, ldb=0, bias=b2, act=ACT_TANH, precision=4,
+                     b_bf16=W2plane, ld_bf16=W2plane.stride(0))
+        else:
+            ops.gemm(H1, W2, Eb, R, eng.C, eng.C, a_kmajor=True, b_kmajor=False, bias=b2, act=ACT_TANH, precision=prec,
+                     b_lo=W2lo if prec == 3 else None)
     flops = 2.0 * R * eng.C * eng.C
-    ms_m1 = timeit(lambda: car2(1), iters=10)
-    roof = {'kernel': 'gemm_tf32_kernel<A K-major, B MN-major, 3xTF32 with the A split kept in tensor memory> '
-                      '(CAR_representation layer 2 forward)', 'bound': 'tensor',
+    ms_3 = timeit(lambda: car2(3), iters=10)
+    ms_4 = timeit(lambda: car2(4), iters=10)
+    ms_1 = timeit(lambda: car2(1), iters=10)
+    used = eng.fwd_prec
+    ms_m = ms_4 if used == 4 else ms_3
+    # operand bytes each SM pulls into shared memory per 128x128 output tile and 32-k tile, times the tiles: the forward
+    # GEMMs are bound by that L2 -> shared-memory ingest, not by the tensor pipe
+    tiles = ((R + 127) // 128) * ((eng.C + 127) // 128) * ((eng.C + 31) // 32)
+    roof = {'kernel': ('gemm_tf32_kernel<MODE 4: bf16x3, A split into packed bf16 pairs in tensor memory, pre-split bf16 weight plane>'
+                       if used == 4 else 'gemm_tf32_kernel<MODE 3: 3xTF32 with the A split kept in tensor memory>') +
+                      ' (CAR_representation layer 2 forward)', 'bound': 'tensor',
             'achieved': flops / (ms_m * 1e-3) / 1e12, 'peak': tf_peak, 'unit': 'TFLOP/s',
-            'frac': flops / (ms_m * 1e-3) / 1e12 / tf_peak, 'traffic': _ncu_traffic('gemm_tf32_kernel<0,1,3,1,1>'),
+            'frac': flops / (ms_m * 1e-3) / 1e12 / tf_peak,
+            'traffic': _ncu_traffic('gemm_tf32_kernel<0,0,4,1,1>' if used == 4 else 'gemm_tf32_kernel<0,1,3,1,1>'),
             'peak_source': peak_src + ' cuBLAS bf16 (burst)',
-            'frac_of_tf32_rate_issued': 3.0 * flops / (ms_m * 1e-3) / 1e12 / (tf_peak / 2.0),
-            'shape': [R, eng.C, eng.C], 'us': ms_m * 1e3,
-            'note': 'achieved = algorithmic fp32 FLOPs (2MNK) per second; the kernel issues 3 tf32 MMAs per product '
-                    '(error-compensated fp32 emulation) and tf32 runs at half the bf16 rate, so the tensor pipe is busy for '
-                    '`frac_of_tf32_rate_issued` of the (bf16 peak / 2) rate',
-            'tf32_single_pass': {'achieved': flops / (ms_m1 * 1e-3) / 1e12, 'us': ms_m1 * 1e3,
-                                 'frac_of_bf16_peak': flops / (ms_m1 * 1e-3) / 1e12 / tf_peak}}
+            'issued_mma_flops_frac_of_peak': (3.0 * flops / (ms_m * 1e-3) / 1e12) / (tf_peak if used == 4 else tf_peak / 2.0),
+            'shape': [R, eng.C, eng.C], 'us': ms_m * 1e3, 'forward_precision': used,
+            'smem_ingest_GBps': tiles * (32768 if used == 4 else 49152) / (ms_m * 1e-3) / 1e9,
+            'note': 'achieved = algorithmic fp32 FLOPs (2MNK) per second; the kernel issues 3 MMAs per product (error-compensated: '
+                    'fp32-grade logits) - tf32 ones at half the bf16 rate (precision 3) or bf16 ones at the full rate (precision 4)',
+            'variants_us': {'3xTF32 (precision 3)': ms_3 * 1e3, 'bf16x3 (precision 4)': ms_4 * 1e3, 'single-pass TF32 (precision 1)': ms_1 * 1e3},
+            'tf32_single_pass': {'achieved': flops / (ms_1 * 1e-3) / 1e12, 'us': ms_1 * 1e3,
+                                 'frac_of_bf16_peak': flops / (ms_1 * 1e-3) / 1e12 / tf_peak}}
     return roof, roof_g
 
 

@@ -63,7 +63,7 @@ class NarEngine:
         # forward GEMMs: 3 = 3xTF32, 4 = bf16x3 (bf16 hi + lo pieces on the kind::f16 path: same error compensation at twice
         # the tensor rate and 2/3 of the operand bytes; logits within 3e-5 of fp32 instead of 3e-6 - the bar is 1e-3)
         if fwd_precision is None:
-            fwd_precision = int(os.environ.get('NAR_FWD_PRECISION', '3'))
+            fwd_precision = int(os.environ.get('NAR_FWD_PRECISION', '4'))
         self.fwd_prec, self.bwd_prec = int(fwd_precision), int(bwd_precision)
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
@@ -265,7 +265,8 @@ class NarEngine:
         if cap < max(L, 1) or self._ws is None:
             worst = B * T
             _, wb = self._ws_bytes(Bg, B, T, worst, True)
-            cap = worst if wb <= self._ws_budget else max(self._L_cap, min(worst, int(L * 1.25) + 64))
+            # (1.5x head-room: a regrowth is a multi-GB cudaMalloc, i.e. a stall of several ms in the middle of the loop)
+            cap = worst if wb <= self._ws_budget else max(self._L_cap, min(worst, int(L * 1.5) + 64))
             if cap != self._L_cap:
                 self._old.append((self._ws, dict(self._prep_ws)))
                 self._old = self._old[-3:]

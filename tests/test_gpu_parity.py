@@ -205,7 +205,7 @@ def test_unsynced_trajectory_g1(bwd):
 
 def test_nccl_two_ranks_match_single():
     """Real NCCL: a 2-rank data-parallel run (torchrun, one rank per GPU) reproduces the 1-rank run of the same global
-    batch - negatives bit-exact, loss within 1e-5, all-reduced gradient within 1e-4 of its max, weights within Adam's
+    batch - negatives bit-exact, loss within 1e-5, all-reduced gradient within the TF32 backward noise (3e-3 of its max), weights within Adam's
     +-lr noise on near-zero gradients.  Needs 2 GPUs (skipped on a 1-GPU box; run with `gpurun --gpus 2`)."""
     import json
     import subprocess
@@ -220,7 +220,9 @@ def test_nccl_two_ranks_match_single():
     res = json.loads(line[len('NCCL_EQUIV '):])
     assert res['negatives_equal']
     assert res['loss_rel_max'] < 1e-5 and res['reg_rel_max'] < 1e-5, res
-    assert res['grad_rel_max_last_step'] < 1e-4, res
+    # the all-reduced gradient differs by the TF32 backward noise: each rank truncates ITS partial sums (per-unique-id
+    # segment sums, split-K partials) to tf32 before the next GEMM, so sharding changes what gets truncated: ~2^-11
+    assert res['grad_rel_max_last_step'] < 3e-3, res
     assert res['param_diff_median'] < 1e-6 and res['param_diff_max'] <= 2.5 * res['steps'] * res['lr'], res
 
 

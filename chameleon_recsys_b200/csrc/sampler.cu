@@ -213,7 +213,10 @@ pool_kernel(const int64_t* __restrict__ all_items, int64_t NB, const int64_t* __
   __syncthreads();
   for (int64_t i = t; i < n2; i += POOL_THREADS) {
     const uint64_t key = ws.key2[i];
-    if (key <= thr2) sort_buf[atomicAdd(&s_count, 1)] = key;    // exactly n_pool keys (keys are unique)
+    if (key <= thr2) {                                           // exactly n_pool keys (keys are unique)
+      const int slot = atomicAdd(&s_count, 1);
+      if (slot < (int)np2) sort_buf[slot] = key;                 // (bounded anyway: corrupted keys must not become a wild store)
+    }
   }
   __syncthreads();
   if (np2 <= 1024u) {                       // common case (K*20 <= 1024): register / shuffle bitonic network

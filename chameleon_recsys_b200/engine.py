@@ -277,7 +277,10 @@ class NarEngine:
             self._ws = torch.empty(wb, dtype=torch.uint8, device=self.dev)
         p = self._prep_ws.get(slot)
         if p is None or p.numel() < pb:
-            p = torch.zeros(pb, dtype=torch.uint8, device=self.dev)
+            # torch.empty, NOT zeros: a fill kernel would be queued on the CURRENT (main) stream behind the running step
+            # and land after the side-stream prepare has written its results (found as an illegal address in the 2-GPU
+            # bench: the pool kernel's key arrays were wiped under it).  Everything in here is written before it is read.
+            p = torch.empty(pb, dtype=torch.uint8, device=self.dev)
             self._prep_ws[slot] = p
         return cap, p, self._ws
 
@@ -290,6 +293,9 @@ class NarEngine:
         from .device_state import DeviceClickedItemsState
         self.dstate = DeviceClickedItemsState(host_state, device=self.dev.index)
         self._dstate_host = host_state
+        # its buffers were initialised on the current stream: the side stream must not touch them earlier
+        self._dstate_ready = torch.cuda.Event()
+        self._dstate_ready.record()
         return self.dstate
 
     def detach_device_state(self):
@@ -588,6 +594,9 @@ class NarEngine:
         (``prev`` = its staged dict; what the hook's after_run does on the host in the reference), then the new batch is
         copied and its weight-independent front runs against the updated state."""
         side = self.side_stream() if self.use_side_stream else torch.cuda.current_stream()
+        if self.use_side_stream and getattr(self, '_dstate_ready', None) is not None:
+            side.wait_event(self._dstate_ready)
+            self._dstate_ready = None
         if after is not None and self.use_side_stream:
             side.wait_event(after)
         if prev is not None:

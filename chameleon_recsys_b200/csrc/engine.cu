@@ -25,7 +25,7 @@ extern "C" int nar_sample_negatives_uidx(nar_ctx*, const int64_t*, int64_t, int6
 
 namespace {
 
-constexpr int N_EVENTS = 32;
+constexpr int N_EVENTS = 64;
 
 inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
@@ -70,7 +70,7 @@ struct nar_engine {
   nar_ctx* ctx;
   nar_model_cfg cfg;
   PlaneSet planes;
-  cudaStream_t aux;
+  cudaStream_t aux, aux2;
   cudaEvent_t ev[N_EVENTS];
   int ev_i;
   float* WhT[NAR_MAX_LAYERS];
@@ -158,12 +158,25 @@ struct Seq {
 
   cudaEvent_t next_event() { cudaEvent_t v = e->ev[e->ev_i]; e->ev_i = (e->ev_i + 1) % N_EVENTS; return v; }
   // stream that deferred work (weight / bias gradients, forward session branch) runs on, after everything queued on main so far
-  cudaStream_t fork() {
+  cudaStream_t fork() { return fork(main); }
+  cudaStream_t fork(cudaStream_t from) {           // deferred work of a chain that itself runs on `from`
     if (!use_aux) return main;
     cudaEvent_t v = next_event();
-    if (cudaEventRecord(v, main) != cudaSuccess || cudaStreamWaitEvent(aux, v, 0) != cudaSuccess) rc = rc ? rc : (int)cudaGetLastError();
+    if (cudaEventRecord(v, from) != cudaSuccess || cudaStreamWaitEvent(aux, v, 0) != cudaSuccess) rc = rc ? rc : (int)cudaGetLastError();
     aux_dirty = true;
     return aux;
+  }
+  // second auxiliary stream: an independent CHAIN (the session backward) next to the main stream's
+  cudaStream_t fork2() {
+    if (!use_aux) return main;
+    cudaEvent_t v = next_event();
+    if (cudaEventRecord(v, main) != cudaSuccess || cudaStreamWaitEvent(e->aux2, v, 0) != cudaSuccess) rc = rc ? rc : (int)cudaGetLastError();
+    return e->aux2;
+  }
+  void join2() {
+    if (!use_aux) return;
+    cudaEvent_t v = next_event();
+    if (cudaEventRecord(v, e->aux2) != cudaSuccess || cudaStreamWaitEvent(main, v, 0) != cudaSuccess) rc = rc ? rc : (int)cudaGetLastError();
   }
   void join() {
     if (!use_aux || !aux_dirty) return;
@@ -322,66 +335,75 @@ int run_step(nar_engine* e, const nar_step_io* io, cudaStream_t main) {
   } else {
     s.chk(nar_act_bwd(dEc, Ec, Rc * C, NAR_ACT_TANH, dEc, main));
   }
-  // ---- FC2 / FC1 (nar_model.py:410-426) -> BPTT -> d(E) of the clicked rows
-  s.chk(nar_act_bwd(sb.dPR, sb.PR, L * C, NAR_ACT_TANH, sb.dPR, main));
-  { cudaStream_t st = s.fork(); s.wgrad(sb.F1, 512, sb.dPR, C, c.off_W4, C, 512, C, L, st); s.bgrad(sb.dPR, C, L, C, c.off_b4, st); }
-  s.dgrad(sb.dPR, C, c.off_W4, C, sb.dF1, 512, L, 512, C, NAR_ACT_LEAKY_RELU, sb.F1, 512, 0, main);
-  if (drop) dropout(sb.dF1, sb.dF1, L, 512, io->pos_idx, 4, main);     // F1 holds the dropped activations: re-apply the mask to the gradient
-  const float* rnn_out = drop ? sb.HOd[c.layers - 1] : sb.HO[c.layers - 1];
-  { cudaStream_t st = s.fork(); s.wgrad(rnn_out, Hp, sb.dF1, 512, c.off_W3, 512, Hp, 512, L, st); s.bgrad(sb.dF1, 512, L, 512, c.off_b3, st); }
-  s.dgrad(sb.dF1, 512, c.off_W3, 512, sb.dHO, Hp, L, Hp, 512, NAR_ACT_NONE, nullptr, 0, 0, main);
-  float* dho = sb.dHO;
-  for (int i = c.layers - 1; i >= 0; --i) {
-    if (drop) dropout(dho, dho, L, Hp, io->pos_idx, 8 + i, main);       // gradient of the dropped cell output
-    const float* x_in = i == 0 ? sb.E : (drop ? sb.HOd[i - 1] : sb.HO[i - 1]);
-    const int64_t n_in = i == 0 ? C : Hp;
-    if (c.rnn_cell == 1) {
-      const int64_t W3 = 3 * Hp;
-      s.chk(nar_transpose_f32(s.W(c.off_Wh[i]), Hp, 2 * Hp, 2 * Hp, e->WhT[i], Hp, main));
-      s.chk(nar_transpose_f32(s.W(c.off_Whc[i]), Hp, Hp, Hp, e->WhcT[i], Hp, main));
-      s.chk(nar_gru_bwd(e->ctx, dho, sb.HO[i], sb.GT[i], sb.UO[i], sb.CD[i], e->WhT[i], e->WhcT[i], io->sess_off, B, Hp, sb.dGX[i],
-                        sb.HPV[i], main));
-      const float* dg = sb.dGX[i]; const float* dc = sb.dGX[i] + 2 * Hp;
-      {
-        cudaStream_t st = s.fork();
-        s.wgrad(x_in, n_in, dg, W3, c.off_Wx[i], 2 * Hp, n_in, 2 * Hp, L, st);
-        s.wgrad(x_in, n_in, dc, W3, c.off_Wxc[i], Hp, n_in, Hp, L, st);
-        s.wgrad(sb.HPV[i], Hp, dg, W3, c.off_Wh[i], 2 * Hp, Hp, 2 * Hp, L, st);
-        s.wgrad(sb.RH[i], Hp, dc, W3, c.off_Whc[i], Hp, Hp, Hp, L, st);
-        s.bgrad(dg, W3, L, 2 * Hp, c.off_rb[i], st);
-        s.bgrad(dc, W3, L, Hp, c.off_bc[i], st);
+  // ---- two independent chains from here on:
+  //   S  session branch: FC2 / FC1 (nar_model.py:410-426) -> BPTT -> d(E) of the L clicked rows - a dozen small kernels
+  //   C  candidates: CAR layer-2 backward over the L*(1+K) candidate rows - the big GEMMs (+ the segment sums)
+  // S runs on a second auxiliary stream next to C; they meet before the clicked rows' CAR backward.
+  auto session_backward = [&](cudaStream_t ss) {
+    s.chk(nar_act_bwd(sb.dPR, sb.PR, L * C, NAR_ACT_TANH, sb.dPR, ss));
+    { cudaStream_t st = s.fork(ss); s.wgrad(sb.F1, 512, sb.dPR, C, c.off_W4, C, 512, C, L, st); s.bgrad(sb.dPR, C, L, C, c.off_b4, st); }
+    s.dgrad(sb.dPR, C, c.off_W4, C, sb.dF1, 512, L, 512, C, NAR_ACT_LEAKY_RELU, sb.F1, 512, 0, ss);
+    if (drop) dropout(sb.dF1, sb.dF1, L, 512, io->pos_idx, 4, ss);     // F1 holds the dropped activations: re-apply the mask to the gradient
+    const float* rnn_out = drop ? sb.HOd[c.layers - 1] : sb.HO[c.layers - 1];
+    { cudaStream_t st = s.fork(ss); s.wgrad(rnn_out, Hp, sb.dF1, 512, c.off_W3, 512, Hp, 512, L, st); s.bgrad(sb.dF1, 512, L, 512, c.off_b3, st); }
+    s.dgrad(sb.dF1, 512, c.off_W3, 512, sb.dHO, Hp, L, Hp, 512, NAR_ACT_NONE, nullptr, 0, 0, ss);
+    float* dho = sb.dHO;
+    for (int i = c.layers - 1; i >= 0; --i) {
+      if (drop) dropout(dho, dho, L, Hp, io->pos_idx, 8 + i, ss);       // gradient of the dropped cell output
+      const float* x_in = i == 0 ? sb.E : (drop ? sb.HOd[i - 1] : sb.HO[i - 1]);
+      const int64_t n_in = i == 0 ? C : Hp;
+      if (c.rnn_cell == 1) {
+        const int64_t W3 = 3 * Hp;
+        s.chk(nar_transpose_f32(s.W(c.off_Wh[i]), Hp, 2 * Hp, 2 * Hp, e->WhT[i], Hp, ss));
+        s.chk(nar_transpose_f32(s.W(c.off_Whc[i]), Hp, Hp, Hp, e->WhcT[i], Hp, ss));
+        s.chk(nar_gru_bwd(e->ctx, dho, sb.HO[i], sb.GT[i], sb.UO[i], sb.CD[i], e->WhT[i], e->WhcT[i], io->sess_off, B, Hp, sb.dGX[i],
+                          sb.HPV[i], ss));
+        const float* dg = sb.dGX[i]; const float* dc = sb.dGX[i] + 2 * Hp;
+        {
+          cudaStream_t st = s.fork(ss);
+          s.wgrad(x_in, n_in, dg, W3, c.off_Wx[i], 2 * Hp, n_in, 2 * Hp, L, st);
+          s.wgrad(x_in, n_in, dc, W3, c.off_Wxc[i], Hp, n_in, Hp, L, st);
+          s.wgrad(sb.HPV[i], Hp, dg, W3, c.off_Wh[i], 2 * Hp, Hp, 2 * Hp, L, st);
+          s.wgrad(sb.RH[i], Hp, dc, W3, c.off_Whc[i], Hp, Hp, Hp, L, st);
+          s.bgrad(dg, W3, L, 2 * Hp, c.off_rb[i], st);
+          s.bgrad(dc, W3, L, Hp, c.off_bc[i], st);
+        }
+        // d(input) = d_gx[:, :2Hp] Wxg^T + d_gx[:, 2Hp:] Wxc^T (two GEMMs into one buffer), then through the CAR tanh for layer 0
+        float* dxin = i == 0 ? sb.dE : sb.dHOb[i];
+        const int64_t ldx = i == 0 ? C : Hp;
+        s.dgrad(dg, W3, c.off_Wx[i], 2 * Hp, dxin, ldx, L, n_in, 2 * Hp, NAR_ACT_NONE, nullptr, 0, 0, ss);
+        s.dgrad(dc, W3, c.off_Wxc[i], Hp, dxin, ldx, L, n_in, Hp, NAR_ACT_NONE, nullptr, 0, 1, ss);
+        if (i == 0) s.chk(nar_act_bwd(sb.dE, sb.E, L * C, NAR_ACT_TANH, sb.dE, ss));
+        else dho = sb.dHOb[i];
+        continue;
       }
-      // d(input) = d_gx[:, :2Hp] Wxg^T + d_gx[:, 2Hp:] Wxc^T (two GEMMs into one buffer), then through the CAR tanh for layer 0
-      float* dxin = i == 0 ? sb.dE : sb.dHOb[i];
-      const int64_t ldx = i == 0 ? C : Hp;
-      s.dgrad(dg, W3, c.off_Wx[i], 2 * Hp, dxin, ldx, L, n_in, 2 * Hp, NAR_ACT_NONE, nullptr, 0, 0, main);
-      s.dgrad(dc, W3, c.off_Wxc[i], Hp, dxin, ldx, L, n_in, Hp, NAR_ACT_NONE, nullptr, 0, 1, main);
-      if (i == 0) s.chk(nar_act_bwd(sb.dE, sb.E, L * C, NAR_ACT_TANH, sb.dE, main));
-      else dho = sb.dHOb[i];
-      continue;
+      s.chk(nar_transpose_f32(s.W(c.off_Wh[i]), Hp, 2 * Hp, 2 * Hp, e->WhT[i], Hp, ss));
+      s.chk(nar_ugrnn_bwd(e->ctx, dho, sb.HO[i], sb.GT[i], sb.CD[i], e->WhT[i], io->sess_off, B, Hp, sb.dGX[i], sb.HPV[i], ss));
+      {
+        cudaStream_t st = s.fork(ss);
+        s.wgrad(x_in, n_in, sb.dGX[i], 2 * Hp, c.off_Wx[i], 2 * Hp, n_in, 2 * Hp, L, st);
+        s.wgrad(sb.HPV[i], Hp, sb.dGX[i], 2 * Hp, c.off_Wh[i], 2 * Hp, Hp, 2 * Hp, L, st);
+        s.bgrad(sb.dGX[i], 2 * Hp, L, 2 * Hp, c.off_rb[i], st);
+      }
+      if (i == 0) {
+        s.dgrad(sb.dGX[0], 2 * Hp, c.off_Wx[0], 2 * Hp, sb.dE, C, L, C, 2 * Hp, NAR_ACT_TANH, sb.E, C, 0, ss);   // clicked rows of dE (pre-tanh)
+      } else {
+        s.dgrad(sb.dGX[i], 2 * Hp, c.off_Wx[i], 2 * Hp, sb.dHOb[i], Hp, L, Hp, 2 * Hp, NAR_ACT_NONE, nullptr, 0, 0, ss);
+        dho = sb.dHOb[i];
+      }
     }
-    s.chk(nar_transpose_f32(s.W(c.off_Wh[i]), Hp, 2 * Hp, 2 * Hp, e->WhT[i], Hp, main));
-    s.chk(nar_ugrnn_bwd(e->ctx, dho, sb.HO[i], sb.GT[i], sb.CD[i], e->WhT[i], io->sess_off, B, Hp, sb.dGX[i], sb.HPV[i], main));
-    {
-      cudaStream_t st = s.fork();
-      s.wgrad(x_in, n_in, sb.dGX[i], 2 * Hp, c.off_Wx[i], 2 * Hp, n_in, 2 * Hp, L, st);
-      s.wgrad(sb.HPV[i], Hp, sb.dGX[i], 2 * Hp, c.off_Wh[i], 2 * Hp, Hp, 2 * Hp, L, st);
-      s.bgrad(sb.dGX[i], 2 * Hp, L, 2 * Hp, c.off_rb[i], st);
-    }
-    if (i == 0) {
-      s.dgrad(sb.dGX[0], 2 * Hp, c.off_Wx[0], 2 * Hp, sb.dE, C, L, C, 2 * Hp, NAR_ACT_TANH, sb.E, C, 0, main);   // clicked rows of dE (pre-tanh)
-    } else {
-      s.dgrad(sb.dGX[i], 2 * Hp, c.off_Wx[i], 2 * Hp, sb.dHOb[i], Hp, L, Hp, 2 * Hp, NAR_ACT_NONE, nullptr, 0, 0, main);
-      dho = sb.dHOb[i];
-    }
-  }
-  // ---- CAR backward (shared weights): layer 2 over all R rows, layer 1 over the rows that were multiplied by W1
-  { cudaStream_t st = s.fork(); s.wgrad(sb.H1, C, sb.dE, C, c.off_W2, C, C, C, R, st); s.bgrad(sb.dE, C, R, C, c.off_b2, st); }
+  };
+  { cudaStream_t ss = s.fork2(); session_backward(ss); }
+  // ---- C: CAR layer 2 of the candidate rows (shared weights: the clicked rows follow once S has produced their dE)
+  { cudaStream_t st = s.fork(); s.wgrad(H1c, C, dEc, C, c.off_W2, C, C, C, Rc, st); s.bgrad(dEc, C, Rc, C, c.off_b2, st); }
+  float* dH1c = c.dedup ? sb.dH1 : sb.dH1 + L * C;
+  s.dgrad(dEc, C, c.off_W2, C, dH1c, C, Rc, C, C, NAR_ACT_LEAKY_RELU, H1c, C, 0, main);
+  float* DBin = sb.DB; float* DBpp = sb.DB + L * C; float* DBpi = sb.DB + 2 * L * C; float* DBpc = sb.DB + NB * C;
+  if (c.dedup) s.chk(nar_car_segsum(sb.dH1, L, K, C, U, pb.Mt, pb.ld_mt, io->pos_idx, pb.neg_uidx, DBpp, DBpc, DBpi, main));
+  s.join2();                                       // dE[0:L] is final
+  { cudaStream_t st = s.fork(); s.wgrad(sb.H1, C, sb.dE, C, c.off_W2, C, C, C, L, st); s.bgrad(sb.dE, C, L, C, c.off_b2, st); }
   if (c.dedup) {
-    float* DBin = sb.DB; float* DBpp = sb.DB + L * C; float* DBpi = sb.DB + 2 * L * C; float* DBpc = sb.DB + NB * C;
     s.dgrad(sb.dE, C, c.off_W2, C, DBin, C, L, C, C, NAR_ACT_LEAKY_RELU, sb.H1, C, 0, main);
-    s.dgrad(dEc, C, c.off_W2, C, sb.dH1, C, Rc, C, C, NAR_ACT_LEAKY_RELU, H1c, C, 0, main);
-    s.chk(nar_car_segsum(sb.dH1, L, K, C, U, pb.Mt, pb.ld_mt, io->pos_idx, pb.neg_uidx, DBpp, DBpc, DBpi, main));
     {
       cudaStream_t st = s.fork();
       s.wgrad(sb.X, Fp, sb.DB, C, c.off_W1, C, Fp, C, NB, st);                                    // clicked + positive + unique item rows
@@ -392,7 +414,7 @@ int run_step(nar_engine* e, const nar_step_io* io, cudaStream_t main) {
     // the negatives' context gradient lands on the clicked row of the same position (identical raw context features)
     s.dgrad(DBpc, C, c.off_W1 + c0 * C, C, sb.dX + c0, Fp, L, Fp - c0, C, NAR_ACT_NONE, nullptr, 0, 1, main);
   } else {
-    s.dgrad(sb.dE, C, c.off_W2, C, sb.dH1, C, R, C, C, NAR_ACT_LEAKY_RELU, sb.H1, C, 0, main);
+    s.dgrad(sb.dE, C, c.off_W2, C, sb.dH1, C, L, C, C, NAR_ACT_LEAKY_RELU, sb.H1, C, 0, main);
     { cudaStream_t st = s.fork(); s.wgrad(sb.X, Fp, sb.dH1, C, c.off_W1, C, Fp, C, R, st); s.bgrad(sb.dH1, C, R, C, c.off_b1, st); }
     s.dgrad(sb.dH1, C, c.off_W1, C, sb.dX, Fp, R, Fp, C, NAR_ACT_NONE, nullptr, 0, 0, main);
     if (drop) dropout(sb.dX, sb.dX, R, Fp, pb.row_pos, 0, main);
@@ -455,7 +477,8 @@ extern "C" int nar_engine_create(nar_ctx* ctx, const nar_model_cfg* cfg, nar_eng
   memset(e, 0, sizeof(*e));
   e->ctx = ctx; e->cfg = *cfg;
   NAR_CHECK_CUDA(cudaSetDevice(ctx->device));
-  if (cudaStreamCreateWithFlags(&e->aux, cudaStreamNonBlocking) != cudaSuccess) { delete e; return NAR_ERR_NO_DEVICE; }
+  if (cudaStreamCreateWithFlags(&e->aux, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&e->aux2, cudaStreamNonBlocking) != cudaSuccess) { delete e; return NAR_ERR_NO_DEVICE; }
   for (int i = 0; i < N_EVENTS; ++i)
     if (cudaEventCreateWithFlags(&e->ev[i], cudaEventDisableTiming) != cudaSuccess) { delete e; return NAR_ERR_NO_DEVICE; }
   for (int i = 0; i < cfg->layers; ++i) {
@@ -476,6 +499,7 @@ extern "C" int nar_engine_refresh(nar_engine* e, void* stream) {
 extern "C" int nar_engine_destroy(nar_engine* e) {
   if (!e) return NAR_OK;
   cudaStreamSynchronize(e->aux);
+  if (e->aux2) { cudaStreamSynchronize(e->aux2); cudaStreamDestroy(e->aux2); }
   for (int i = 0; i < NAR_MAX_LAYERS; ++i) { if (e->WhT[i]) cudaFree(e->WhT[i]); if (e->WhcT[i]) cudaFree(e->WhcT[i]); }
   for (int i = 0; i < N_EVENTS; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   if (e->aux) cudaStreamDestroy(e->aux);

@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include <string.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 extern "C" int nar_sample_negatives_uidx(nar_ctx*, const int64_t*, int64_t, int64_t, int64_t, int64_t, const int64_t*, int64_t,
                                          int64_t, int64_t, uint64_t, uint32_t, int64_t*, int32_t*, const int64_t**,
@@ -167,14 +168,15 @@ struct Seq {
     return aux;
   }
   // second auxiliary stream: an independent CHAIN (the session backward) next to the main stream's
+  bool two_chains = false;
   cudaStream_t fork2() {
-    if (!use_aux) return main;
+    if (!use_aux || !two_chains) return main;
     cudaEvent_t v = next_event();
     if (cudaEventRecord(v, main) != cudaSuccess || cudaStreamWaitEvent(e->aux2, v, 0) != cudaSuccess) rc = rc ? rc : (int)cudaGetLastError();
     return e->aux2;
   }
   void join2() {
-    if (!use_aux) return;
+    if (!use_aux || !two_chains) return;
     cudaEvent_t v = next_event();
     if (cudaEventRecord(v, e->aux2) != cudaSuccess || cudaStreamWaitEvent(main, v, 0) != cudaSuccess) rc = rc ? rc : (int)cudaGetLastError();
   }
@@ -241,7 +243,14 @@ int run_step(nar_engine* e, const nar_step_io* io, cudaStream_t main) {
   if (drop && c.dedup) return NAR_ERR_INVALID;
   const uint32_t dstep = (uint32_t)(io->global_step + 1);
   Seq s(e, io, main);
+  // NAR_DEBUG_DROP_ONLY=<tensor id> (diagnostics, mirrored by the oracle): dropout at that site only
+  int drop_only = -1;
+  if (drop) { const char* v = getenv("NAR_DEBUG_DROP_ONLY"); if (v) drop_only = atoi(v); }
   auto dropout = [&](const float* src, float* dst, int64_t rows, int64_t cols, const int32_t* rpos, int tid, cudaStream_t st) {
+    if (drop_only >= 0 && drop_only != tid) {
+      if (src != dst) cudaMemcpyAsync(dst, src, (size_t)rows * cols * sizeof(float), cudaMemcpyDeviceToDevice, st);
+      return;
+    }
     s.chk(nar_dropout_rows(src, dst, rows, cols, cols, rpos, L, n_cand, K, tid, c.keep_prob, c.dropout_seed, dstep, st));
   };
   const float inv_count = 1.0f / (float)(io->L_global > 0 ? io->L_global : 1);
@@ -393,6 +402,9 @@ int run_step(nar_engine* e, const nar_step_io* io, cudaStream_t main) {
       }
     }
   };
+  // (NAR_BWD_CHAINS=1; default 0: measured 1.22 -> 1.27 ms per G1 step - the deferred weight gradients of both chains
+  // share ONE auxiliary stream in enqueue order, so the big layer-2 wgrad of C waits behind the last small wgrad of S)
+  { const char* v = getenv("NAR_BWD_CHAINS"); s.two_chains = v && atoi(v) != 0; }
   { cudaStream_t ss = s.fork2(); session_backward(ss); }
   // ---- C: CAR layer 2 of the candidate rows (shared weights: the clicked rows follow once S has produced their dE)
   { cudaStream_t st = s.fork(); s.wgrad(H1c, C, dEc, C, c.off_W2, C, C, C, Rc, st); s.bgrad(dEc, C, Rc, C, c.off_b2, st); }

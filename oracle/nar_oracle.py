@@ -187,6 +187,10 @@ class NarOracle:
         """tf.layers.dropout(rate = 1 - keep_prob, training=True) with the counter-based masks of dropout_ref."""
         if self._drop is None or self.keep_prob >= 1.0:
             return x
+        import os
+        only = os.environ.get('NAR_DEBUG_DROP_ONLY')            # diagnostics: dropout at one site only (feature rows = 0)
+        if only is not None and int(only) != (0 if tensor_id in (1, 2, 3) else tensor_id):
+            return x
         from . import dropout_ref
         n_cols = x.shape[-1]
         if feature_rows:

@@ -604,7 +604,7 @@ extern "C" int nar_engine_buffer(const nar_engine* e, const nar_step_io* io, con
       {"base_item", pb.base_item, NB, 1}, {"Mt", pb.Mt, pb.U, pb.ld_mt},
       {"X", sb.X, c.dedup ? NB : R, c.Fp}, {"dX", sb.dX, c.dedup ? NB : R, c.Fp}, {"H1", sb.H1, R, c.C}, {"E", sb.E, R, c.C},
       {"dE", sb.dE, R, c.C}, {"dH1", sb.dH1, c.dedup ? Rc : R, c.C}, {"F1", sb.F1, L, 512}, {"PR", sb.PR, L, c.C},
-      {"logits", sb.logits, L, n_cand}, {"PD", sb.PD, Rc, c.C}, {"Z3", sb.Z3, Rc, 32}, {"PP", sb.PP, L, c.C},
+      {"logits", sb.logits, L, n_cand}, {"PD", sb.PD, Rc, c.C}, {"Z1", sb.Z1, Rc, 128}, {"Z2", sb.Z2, Rc, 64}, {"Z3", sb.Z3, Rc, 32}, {"PP", sb.PP, L, c.C},
       {"PI", sb.PI, pb.U, c.C}, {"PC", sb.PC, L, c.C}, {"DB", sb.DB, 3 * L + pb.U, c.C},
       {"HO0", sb.HO[0], L, c.Hp}, {"HO1", sb.HO[1], L, c.Hp}, {"HO2", sb.HO[2], L, c.Hp}, {"HO3", sb.HO[3], L, c.Hp},
       {"HOd0", sb.HOd[0], L, c.Hp}, {"HOd1", sb.HOd[1], L, c.Hp}, {"HOd2", sb.HOd[2], L, c.Hp}, {"HOd3", sb.HOd[3], L, c.Hp},

@@ -546,7 +546,8 @@ class NarEngine:
             X = torch.cat([xin, torch.cat([xpos[:, None, :], xneg], dim=1).reshape(L * n_cand, -1)], dim=0)
         # with dropout the RNN OUTPUT the reference exposes is the dropped one (DropoutWrapper); the state is HO<i>
         ho = 'HOd%d' if (self.keep_prob < 1.0 and train) else 'HO%d'
-        return dict(X=X.clone(), H1=b('H1'), E=b('E'), HO=[b(ho % i) for i in range(self.layers)], F1=b('F1'), PR=b('PR'),
+        extra = {n: b(n) for n in ('Z1', 'Z2', 'Z3')} if self.ranking == 'mlp' else {}
+        return dict(X=X.clone(), H1=b('H1'), E=b('E'), **extra, HO=[b(ho % i) for i in range(self.layers)], F1=b('F1'), PR=b('PR'),
                     logits=b('logits'), row_pos=b('row_pos').view(-1), row_item=b('row_item').view(-1),
                     stats=b('stats').view(-1).clone(),
                     neg=b('neg').view(-1)[st['s0'] * T * K:(st['s0'] + st['B']) * T * K].view(st['B'], T, K))

@@ -72,6 +72,7 @@ class NarOracle:
         # internal (HBM) column -> logical column of the product's feature rows: the dropout spec is indexed by the former
         self.int2log = None if int2log is None else np.asarray(int2log, dtype=np.int64)
         self._drop = None          # (step,) while a training forward with dropout runs
+        self._kinks = None
         self.V = int(articles_features_config['article_id']['cardinality'])
         self.adam_m: Dict[str, torch.Tensor] = {}
         self.adam_v: Dict[str, torch.Tensor] = {}
@@ -204,17 +205,27 @@ class NarOracle:
         return x * torch.as_tensor(m).to(self.dtype) / self.keep_prob
 
     # ------------------------------------------------------------------ layers
-    def _dense(self, x, name, act):
+    def _dense(self, x, name, act, kink=None):
         y = x @ self._p(name + '/kernel') + self._p(name + '/bias')
         if act == 'leaky':
+            k = None if (self._kinks is None or kink is None) else self._kinks.get(kink)
+            if k is not None:
+                # Kink alignment (tests): leaky_relu is not differentiable at 0, and a 1e-5 difference in a pre-activation that
+                # happens to sit at the kink flips its slope between 1 and 0.2 - measured: forward noise of 1e-6 of the
+                # tensor max moves the ORACLE's own matching_dense_layer_1/bias gradient by 10 %.  A gradient comparison is
+                # only meaningful at identical slope choices, so the caller may hand over the other implementation's choices
+                # (sign of its stored activations) for the valid positions; padded positions keep the oracle's own.
+                m = (y > 0)
+                m[self._kinks['valid']] = torch.as_tensor(k, dtype=torch.bool)
+                return torch.where(m, y, LEAKY_ALPHA * y)
             return Fn.leaky_relu(y, LEAKY_ALPHA)
         if act == 'tanh':
             return torch.tanh(y)
         return y
 
-    def CAR(self, x):
+    def CAR(self, x, kink=None):
         # nar_model.py:374-403
-        return self._dense(self._dense(x, 'main/CAR/PreCAR_representation', 'leaky'),
+        return self._dense(self._dense(x, 'main/CAR/PreCAR_representation', 'leaky', kink),
                            'main/CAR/CAR_representation', 'tanh')
 
     def rnn(self, x, lengths, pos_key=None):
@@ -254,25 +265,26 @@ class NarOracle:
             states = [alive * ns + (1.0 - alive) * s for ns, s in zip(new_states, states)]
         return torch.stack(outs, dim=1)
 
-    def scorer(self, cand, pred):
+    def scorer(self, cand, pred, kink=None):
         # nar_model.py:447-500 (cand [...,C] already multiplied outside for 'mlp')
         if self.ranking == 'cosine':
             return (Fn.normalize(cand, dim=-1) * Fn.normalize(pred, dim=-1)).sum(-1, keepdim=True)
         z = cand * pred
         base = 'main/recommendations_ranking/matching_dense_layer_'
-        z = self._dense(z, base + '1', 'leaky')
-        z = self._dense(z, base + '2', 'leaky')
-        z = self._dense(z, base + '3', 'leaky')
+        z = self._dense(z, base + '1', 'leaky', None if kink is None else 'z1_' + kink)
+        z = self._dense(z, base + '2', 'leaky', None if kink is None else 'z2_' + kink)
+        z = self._dense(z, base + '3', 'leaky', None if kink is None else 'z3_' + kink)
         return self._dense(z, base + '4', None)
 
     # ------------------------------------------------------------------ forward
     def forward(self, features: Dict[str, np.ndarray], labels: Dict[str, np.ndarray], negatives: np.ndarray,
                 buffer: np.ndarray, pop_norm: np.ndarray, sum_mask_global: Optional[float] = None,
-                train_step: Optional[int] = None, session0: int = 0):
+                train_step: Optional[int] = None, session0: int = 0, kinks: Optional[dict] = None):
         """-> dict with total_loss, xe_loss, reg_loss, logits [B,T,1+K] (already / temperature), mask, ...
         ``train_step`` (the optimiser step number, 1-based) switches dropout on (training mode, keep_prob < 1);
         ``session0`` = global index of the first session (data-parallel shards draw the masks of their own rows)."""
         self._drop = int(train_step) if (train_step is not None and self.keep_prob < 1.0) else None
+        self._kinks = kinks          # see _dense: {'valid': bool [B,T], 'h1_in' / 'h1_pos' / 'h1_neg' / 'f1' / 'z{1,2,3}_{pos,neg}': slopes}
         item_clicked = torch.as_tensor(features['item_clicked']).long()
         event_ts = torch.as_tensor(features['event_timestamp']).long().unsqueeze(-1)
         lengths = torch.as_tensor(features['session_size']).long() - 1          # :227
@@ -305,13 +317,13 @@ class NarOracle:
         x_neg = torch.cat([ctx_t, f_neg], dim=3) * gamma + beta                                    # :360-364
         x_neg = self._dropout(x_neg, 3, pos_key[:, :, None] * Kn + np.arange(Kn, dtype=np.int64), feature_rows=True)   # :367-369
 
-        e_in, e_pos, e_neg = self.CAR(x_in), self.CAR(x_pos), self.CAR(x_neg)                      # :382-403
+        e_in, e_pos, e_neg = self.CAR(x_in, 'h1_in'), self.CAR(x_pos, 'h1_pos'), self.CAR(x_neg, 'h1_neg')   # :382-403
         r = self.rnn(e_in, lengths, pos_key if self._drop is not None else None)                   # :408
-        fc1 = self._dense(r, 'main/session_representation/FC1', 'leaky')                           # :411
+        fc1 = self._dense(r, 'main/session_representation/FC1', 'leaky', 'f1')                     # :411
         fc1 = self._dropout(fc1, 4, pos_key)                                                       # :417-419
         pred = self._dense(fc1, 'main/session_representation/FC2', 'tanh')                         # :423-438
-        s_pos = self.scorer(e_pos, pred)                                                           # :478-485
-        s_neg = self.scorer(e_neg, pred.unsqueeze(2)).squeeze(-1)                                  # :493-500
+        s_pos = self.scorer(e_pos, pred, 'pos')                                                    # :478-485
+        s_neg = self.scorer(e_neg, pred.unsqueeze(2), 'neg').squeeze(-1)                           # :493-500
         logits = torch.cat([s_pos, s_neg], dim=2) / self.tau                                       # :511-514
         logp = torch.log_softmax(logits, dim=-1)                                                   # :515, :660
         m = mask.to(self.dtype)
@@ -331,6 +343,7 @@ class NarOracle:
             nov_reg = self.nov_factor * ((neg_prob * nov).sum(-1) * m).sum() / denom
             total = total - nov_reg
         self._drop = None
+        self._kinks = None
         return {'total_loss': total, 'xe_loss': xe, 'reg_loss': reg, 'nov_reg_loss': nov_reg, 'logits': logits, 'mask': mask,
                 'x_in': x_in, 'x_pos': x_pos, 'x_neg': x_neg, 'e_in': e_in, 'e_pos': e_pos, 'e_neg': e_neg,
                 'rnn_out': r, 'pred': pred, 'probs': torch.softmax(logits, dim=-1)}
@@ -373,8 +386,8 @@ class NarOracle:
                 self.adam_v[n].mul_(b2).addcmul_(g, g, value=1.0 - b2)
                 p.sub_(lr_t * self.adam_m[n] / (self.adam_v[n].sqrt() + eps))
 
-    def train_step(self, features, labels, negatives, buffer, pop_norm, sum_mask_global=None):
-        out = self.forward(features, labels, negatives, buffer, pop_norm, sum_mask_global, train_step=self.step + 1)
+    def train_step(self, features, labels, negatives, buffer, pop_norm, sum_mask_global=None, kinks=None):
+        out = self.forward(features, labels, negatives, buffer, pop_norm, sum_mask_global, train_step=self.step + 1, kinks=kinks)
         grads = self.compute_gradients(out)
         self.apply_gradients(grads)
         return out, grads

@@ -1,7 +1,10 @@
 """GPU parity tests (pytest -m gpu): the CUDA path, called through the C ABI (ops.py -> libnar_b200.so),
 against the oracle / fp64 references on the same seeded inputs.
 
-Tolerances (north_star): sampled negatives bit-exact; loss and logits within 1e-3 relative.  Additional bars we
+Tolerances (north_star): sampled negatives bit-exact; loss and logits within 1e-3 relative.  Gradients are compared at
+IDENTICAL leaky_relu slope choices (tools/gpu_step_check.py hands the engine's activation signs to the oracle): a 1e-5
+forward difference that flips one pre-activation across the kink moves the oracle's own bias gradients by up to 10 %
+(tools/debug_drop.py), which says nothing about either implementation.  Additional bars we
 hold ourselves to: feature rows 1e-5, 3xTF32 GEMM 2e-5, TF32 GEMM 3e-3, gradients 3e-2 of the tensor max
 (backward GEMMs run single-pass TF32), Adam update within 0.2*lr where the gradient is far above eps.
 """
@@ -94,10 +97,7 @@ def _check_steps(res, grad_tol=3e-2, update_tol=0.2):
 
 
 @pytest.mark.parametrize('case', ['tinyA', 'tinyB', 'tinyB_cold', 'tinyB_cos', 'tinyB_2l', 'tinyB_nov', 'tinyB_cos_nov', 'tinyB_drop',
-                                  pytest.param('tinyB_2l_drop', marks=pytest.mark.xfail(strict=False, reason='open: two RNN layers + dropout: '
-                                               'the gradients of isolated steps differ from the oracle by up to 10 % of the tensor max '
-                                               '(forward exact; tools/debug_drop.py; DESIGN.md section 3)')),
-                                  'tinyB_pad', 'tinyB_gru', 'tinyB_gru_2l_drop', 'tinyB_gru_cos', 'tinyB_bf16',
+                                  'tinyB_2l_drop', 'tinyB_pad', 'tinyB_gru', 'tinyB_gru_2l_drop', 'tinyB_gru_cos', 'tinyB_bf16',
                                   'tinyA_bf16', 'tinyB_gru_bf16'])
 def test_full_step_parity_tiny(case):
     import torch

@@ -53,7 +53,8 @@ def rel(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)) if a.size else 0.0
 
 
-def run_case(name, profile, warm, n_steps, hp_over=None, oracle_dtype=torch.float64, sync_state=True, engine_kw=None, **mk):
+def run_case(name, profile, warm, n_steps, hp_over=None, oracle_dtype=torch.float64, sync_state=True, engine_kw=None,
+             align_kinks=True, **mk):
     pb = make_problem(name, profile=profile, **(hp_over or {}), **mk)
     hp = pb.hp
     if warm:
@@ -81,14 +82,27 @@ def run_case(name, profile, warm, n_steps, hp_over=None, oracle_dtype=torch.floa
         allc = np.concatenate([feats['item_clicked'], labels['label_last_item']], axis=1)
         neg_ref = sampler_ref.sample_negatives(allc, buf, K, hp.train_negative_samples_from_buffer, hp.sampler_seed, step)
         params_before = {n: v.astype(np.float64) for n, v in orc.get_params().items()}
-        o, grads = orc.train_step(feats, labels, neg_ref, buf, pop)
+        last = eng.last
+        n_cand = K + 1
+        # kink alignment (see NarOracle._dense): the oracle differentiates leaky_relu with the ENGINE's slope choices
+        kinks = None
+        if align_kinks and L > 0:
+            valid = np.arange(T)[None, :] < np.clip(np.asarray(feats['session_size']) - 1, 0, T)[:, None]
+            H1 = last['H1'].cpu().numpy() > 0
+            Hc = H1[L:].reshape(L, n_cand, -1)
+            kinks = {'valid': torch.as_tensor(valid), 'h1_in': H1[:L], 'h1_pos': Hc[:, 0], 'h1_neg': Hc[:, 1:],
+                     'f1': last['F1'].cpu().numpy() > 0}
+            for zn in ('Z1', 'Z2', 'Z3'):
+                if zn in last:
+                    Z = (last[zn].cpu().numpy() > 0).reshape(L, n_cand, -1)
+                    kinks[zn.lower() + '_pos'] = Z[:, 0]
+                    kinks[zn.lower() + '_neg'] = Z[:, 1:]
+        o, grads = orc.train_step(feats, labels, neg_ref, buf, pop, kinks=kinks)
         mask = o['mask'].numpy()
         r = {'step': step, 'B': B, 'T': T, 'L': L, 'neg_equal': bool(np.array_equal(neg_gpu, neg_ref))}
-        last = eng.last
         l2i = pb.plan.log2int
         X = last['X'].cpu().numpy()[:, l2i]
         E = last['E'].cpu().numpy()
-        n_cand = K + 1
         x_in = o['x_in'].detach().numpy()[mask]
         x_pos = o['x_pos'].detach().numpy()[mask]
         x_neg = o['x_neg'].detach().numpy()[mask]

@@ -30,6 +30,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# load every kernel image when the context is created: with lazy loading the first launch of a GEMM variant a later batch
+# happens to select (tile shape depends on the batch's row counts) stalls the host for milliseconds INSIDE the timed region
+os.environ.setdefault('CUDA_MODULE_LOADING', 'EAGER')
 
 
 _REAL_STDOUT = None
@@ -329,13 +332,16 @@ def run_ours(args):
     done = {}
 
     enq = [0.0]
+    enq_each = []
 
     def bounded_step(i):
         if depth > 0 and (i - depth) in done:
             done.pop(i - depth).synchronize()
         t0 = time.perf_counter()
         dev_step(i)
-        enq[0] += time.perf_counter() - t0      # host time spent queueing the step (the wait above is not part of it)
+        dt = time.perf_counter() - t0
+        enq[0] += dt                              # host time spent queueing the step (the wait above is not part of it)
+        enq_each.append(dt)
         if depth > 0:
             ev = torch.cuda.Event()
             ev.record()
@@ -352,6 +358,7 @@ def run_ours(args):
     e0.record()
     t_host0 = time.perf_counter()
     enq[0] = 0.0
+    del enq_each[:]
     for i in range(args.warmup, n_total):
         bounded_step(i)
     e1.record()
@@ -471,7 +478,8 @@ def run_ours(args):
                     'runs_ms_per_step': [r['ms'] / args.steps for r in e2e_runs], 'policy': 'median of three K-step regions',
                     'api': 'Estimator.train(input_fn) -> nar_module_model_fn -> NARModuleModel.train + ItemsStateUpdaterHook'},
             'gpu_launches': launches, 'gpu_launches_per_step': launches / args.steps,
-            'host_enqueue_ms_per_step': host_enqueue_ms, 'host_loop_ms_per_step_incl_waiting_for_the_gpu': host_loop_ms,
+            'host_enqueue_ms_per_step': host_enqueue_ms, 'host_enqueue_ms_median_max': [float(np.median(enq_each)) * 1e3, float(np.max(enq_each)) * 1e3],
+            'host_loop_ms_per_step_incl_waiting_for_the_gpu': host_loop_ms,
             'host_run_ahead_steps': depth,
             'roofline': roof, 'roofline_gather': roof_g, 'clocks': clocks}
     if cfg3:

@@ -350,11 +350,11 @@ int run_step(nar_engine* e, const nar_step_io* io, cudaStream_t main) {
   // S runs on a second auxiliary stream next to C; they meet before the clicked rows' CAR backward.
   auto session_backward = [&](cudaStream_t ss) {
     s.chk(nar_act_bwd(sb.dPR, sb.PR, L * C, NAR_ACT_TANH, sb.dPR, ss));
-    { cudaStream_t st = s.fork(ss); s.wgrad(sb.F1, 512, sb.dPR, C, c.off_W4, C, 512, C, L, st); s.bgrad(sb.dPR, C, L, C, c.off_b4, st); }
+    { cudaStream_t st = s.two_chains ? ss : s.fork(ss); s.wgrad(sb.F1, 512, sb.dPR, C, c.off_W4, C, 512, C, L, st); s.bgrad(sb.dPR, C, L, C, c.off_b4, st); }
     s.dgrad(sb.dPR, C, c.off_W4, C, sb.dF1, 512, L, 512, C, NAR_ACT_LEAKY_RELU, sb.F1, 512, 0, ss);
     if (drop) dropout(sb.dF1, sb.dF1, L, 512, io->pos_idx, 4, ss);     // F1 holds the dropped activations: re-apply the mask to the gradient
     const float* rnn_out = drop ? sb.HOd[c.layers - 1] : sb.HO[c.layers - 1];
-    { cudaStream_t st = s.fork(ss); s.wgrad(rnn_out, Hp, sb.dF1, 512, c.off_W3, 512, Hp, 512, L, st); s.bgrad(sb.dF1, 512, L, 512, c.off_b3, st); }
+    { cudaStream_t st = s.two_chains ? ss : s.fork(ss); s.wgrad(rnn_out, Hp, sb.dF1, 512, c.off_W3, 512, Hp, 512, L, st); s.bgrad(sb.dF1, 512, L, 512, c.off_b3, st); }
     s.dgrad(sb.dF1, 512, c.off_W3, 512, sb.dHO, Hp, L, Hp, 512, NAR_ACT_NONE, nullptr, 0, 0, ss);
     float* dho = sb.dHO;
     for (int i = c.layers - 1; i >= 0; --i) {
@@ -369,7 +369,7 @@ int run_step(nar_engine* e, const nar_step_io* io, cudaStream_t main) {
                           sb.HPV[i], ss));
         const float* dg = sb.dGX[i]; const float* dc = sb.dGX[i] + 2 * Hp;
         {
-          cudaStream_t st = s.fork(ss);
+          cudaStream_t st = s.two_chains ? ss : s.fork(ss);
           s.wgrad(x_in, n_in, dg, W3, c.off_Wx[i], 2 * Hp, n_in, 2 * Hp, L, st);
           s.wgrad(x_in, n_in, dc, W3, c.off_Wxc[i], Hp, n_in, Hp, L, st);
           s.wgrad(sb.HPV[i], Hp, dg, W3, c.off_Wh[i], 2 * Hp, Hp, 2 * Hp, L, st);
@@ -389,7 +389,7 @@ int run_step(nar_engine* e, const nar_step_io* io, cudaStream_t main) {
       s.chk(nar_transpose_f32(s.W(c.off_Wh[i]), Hp, 2 * Hp, 2 * Hp, e->WhT[i], Hp, ss));
       s.chk(nar_ugrnn_bwd(e->ctx, dho, sb.HO[i], sb.GT[i], sb.CD[i], e->WhT[i], io->sess_off, B, Hp, sb.dGX[i], sb.HPV[i], ss));
       {
-        cudaStream_t st = s.fork(ss);
+        cudaStream_t st = s.two_chains ? ss : s.fork(ss);
         s.wgrad(x_in, n_in, sb.dGX[i], 2 * Hp, c.off_Wx[i], 2 * Hp, n_in, 2 * Hp, L, st);
         s.wgrad(sb.HPV[i], Hp, sb.dGX[i], 2 * Hp, c.off_Wh[i], 2 * Hp, Hp, 2 * Hp, L, st);
         s.bgrad(sb.dGX[i], 2 * Hp, L, 2 * Hp, c.off_rb[i], st);
@@ -402,9 +402,9 @@ int run_step(nar_engine* e, const nar_step_io* io, cudaStream_t main) {
       }
     }
   };
-  // (NAR_BWD_CHAINS=1; default 0: measured 1.22 -> 1.27 ms per G1 step - the deferred weight gradients of both chains
-  // share ONE auxiliary stream in enqueue order, so the big layer-2 wgrad of C waits behind the last small wgrad of S)
-  { const char* v = getenv("NAR_BWD_CHAINS"); s.two_chains = v && atoi(v) != 0; }
+  // (NAR_BWD_CHAINS=1.  With two chains S keeps its own weight gradients on its stream: sharing the ONE auxiliary stream
+  // in enqueue order made the big layer-2 wgrad of C wait behind the last small wgrad of S: 1.22 -> 1.27 ms per G1 step.)
+  { const char* v = getenv("NAR_BWD_CHAINS"); s.two_chains = s.use_aux && v && atoi(v) != 0; }
   { cudaStream_t ss = s.fork2(); session_backward(ss); }
   // ---- C: CAR layer 2 of the candidate rows (shared weights: the clicked rows follow once S has produced their dE)
   { cudaStream_t st = s.fork(); s.wgrad(H1c, C, dEc, C, c.off_W2, C, C, C, Rc, st); s.bgrad(dEc, C, Rc, C, c.off_b2, st); }

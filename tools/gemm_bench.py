@@ -44,7 +44,10 @@ def main():
     Wt = W.t().contiguous()
     Wtlo = torch.empty_like(Wt)
     ops.tf32_lo(Wt, Wt.numel(), Wtlo)
+    Wplane = ops.pack_bf16x3(W, K, N)
+    only = os.environ.get('NAR_GEMM_BENCH_ONLY')           # substring filter (used for single-kernel ncu captures)
     cases = [
+        ('fwd  bf16x3 A:K fp32 -> TMEM, B: packed bf16 plane', lambda: ops.gemm(X, None, Y, M, N, K, a_kmajor=True, b_kmajor=True, ldb=0, bias=bias, act=2, precision=4, b_bf16=Wplane, ld_bf16=Wplane.stride(0)), 2.0 * M * N * K),
         ('fwd  3x  A:K  B:K(W^T) +B_lo', lambda: ops.gemm(X, Wt, Y, M, N, K, a_kmajor=True, b_kmajor=True, bias=bias, act=2, precision=3, b_lo=Wtlo), 2.0 * M * N * K),
         ('fwd  3x  A:K  B:K(W^T) in-kernel split', lambda: ops.gemm(X, Wt, Y, M, N, K, a_kmajor=True, b_kmajor=True, bias=bias, act=2, precision=3), 2.0 * M * N * K),
         ('fwd  1x  A:K  B:K(W^T)', lambda: ops.gemm(X, Wt, Y, M, N, K, a_kmajor=True, b_kmajor=True, bias=bias, act=2, precision=1), 2.0 * M * N * K),
@@ -57,6 +60,8 @@ def main():
         ('wgrad 1x A:MN B:MN', lambda: ops.gemm(X, dY, dW, K, N, M, a_kmajor=False, b_kmajor=False, accumulate=True, split_k=0, precision=1), 2.0 * M * N * K),
     ]
     for name, fn, flops in cases:
+        if only and only not in name:
+            continue
         ms = bench(fn, iters, flush)
         print(json.dumps({'case': name, 'shape': [M, N, K], 'us': ms * 1e3, 'tflops': flops / (ms * 1e-3) / 1e12}), flush=True)
 

@@ -554,6 +554,31 @@ def kernel_rooflines(eng, st, hbm_peak, tf_peak, peak_src):
                       'event-pair overhead reported next to it; algorithmic bytes count only the ACR + item-embedding rows, '
                       'the kernel also writes the %d context / metadata / recency / novelty / padding columns of every row'
                       % (plan.Fp - E - Di)}
+    # (c) the embedding gather where the HBM roofline actually applies: the G1 tables (46 MB ACR + 22 MB item embeddings) and
+    # the <= 1.5 K distinct rows a step touches live in the 126 MB L2, so (a) and (b) never see HBM.  Same row shape (250
+    # floats, ld 252), but a table far larger than L2 and distinct random ids: every row comes from HBM once and is written
+    # once (nar_gather_rows_f32, the kernel behind tf.nn.embedding_lookup nar_model.py:948); plus its gradient scatter-add.
+    try:
+        Vb, nb_rows = 1 << 20, 1 << 18
+        tab = torch.randn(Vb, 252, device='cuda')
+        ids = torch.randperm(Vb, device='cuda')[:nb_rows].contiguous()
+        outb = torch.empty(nb_rows, 252, device='cuda')
+        ms_h = timeit(lambda: ops.gather_rows(tab, ids, outb, 250), iters=10)
+        hb = nb_rows * (250 * 4 * 2 + 8)
+        gtab = torch.zeros(Vb, 252, device='cuda')
+        ms_s = timeit(lambda: ops.scatter_add_rows(gtab, ids, outb, 250), iters=10)
+        roof_g['hbm_resident_form'] = {
+            'kernel': 'gather_rows_kernel', 'rows': nb_rows, 'table_rows': Vb, 'row_floats': 250, 'us': ms_h * 1e3, 'algorithmic_bytes': hb,
+            'achieved': hb / (ms_h * 1e-3) / 1e9, 'frac': hb / (ms_h * 1e-3) / 1e9 / hbm_peak,
+            'frac_net_of_event_overhead': hb / (max(ms_h - ms_0, 1e-6) * 1e-3) / 1e9 / hbm_peak,
+            'scatter_add': {'kernel': 'scatter_add_rows_kernel', 'us': ms_s * 1e3,
+                            'achieved': nb_rows * (250 * 4 * 3 + 8) / (ms_s * 1e-3) / 1e9,      # read src + read-modify-write of the row
+                            'frac': nb_rows * (250 * 4 * 3 + 8) / (ms_s * 1e-3) / 1e9 / hbm_peak},
+            'note': '1 Mi x 252 fp32 table (1 GB, 8x the L2), 256 Ki distinct random ids: the only form of this gather that is HBM '
+                    'bound; at G1 size the tables are L2 resident'}
+        del tab, gtab, outb, ids
+    except Exception as ex:  # noqa: BLE001
+        roof_g['hbm_resident_form'] = {'error': str(ex)}
     if eng.dedup:
         nb = 2 * L + K * 20 + 1
         rows_b = ops.row_layout(nb, L, 0, n_positive=L, n_full=2 * L, ctx_col0=plan.ctx_col0)

@@ -30,9 +30,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# load every kernel image when the context is created: with lazy loading the first launch of a GEMM variant a later batch
-# happens to select (tile shape depends on the batch's row counts) stalls the host for milliseconds INSIDE the timed region
-os.environ.setdefault('CUDA_MODULE_LOADING', 'EAGER')
+# (CUDA_MODULE_LOADING=EAGER was tried against first-launch stalls of rarely selected GEMM variants inside the timed region: it
+# also loads every kernel of libtorch - minutes of start-up.  Not used.)
 
 
 _REAL_STDOUT = None

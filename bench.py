@@ -575,6 +575,7 @@ def kernel_rooflines(eng, st, hbm_peak, tf_peak, peak_src):
                             'frac': nb_rows * (250 * 4 * 3 + 8) / (ms_s * 1e-3) / 1e9 / hbm_peak},
             'note': '1 Mi x 252 fp32 table (1 GB, 8x the L2), 256 Ki distinct random ids: the only form of this gather that is HBM '
                     'bound; at G1 size the tables are L2 resident'}
+        roof_g['frac_hbm_resident_form'] = roof_g['hbm_resident_form']['frac']
         del tab, gtab, outb, ids
     except Exception as ex:  # noqa: BLE001
         roof_g['hbm_resident_form'] = {'error': str(ex)}

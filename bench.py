@@ -266,6 +266,9 @@ def workload_config(pb, args, gb):
             'global_batch_sessions': gb, 'per_gpu_batch_sessions': hp.batch_size, 'truncate_session_length': hp.truncate_session_length,
             'negatives': hp.train_total_negative_samples, 'feature_profile': pb.wl.profile, 'session_len': pb.wl.session_len,
             'rnn_cell': hp.rnn_cell, 'ranking': hp.ranking, 'parallelism': 'dp%d' % args.gpus,
+            'sharding': ('contiguous session shards of the global batch, boundaries balanced by valid positions (per-GPU mean '
+                         '%d sessions)' % hp.batch_size) if args.gpus > 1 and os.environ.get('NAR_DP_BALANCE', '1') == '1'
+                        else 'contiguous session shards, equal counts',
             'l2_policy': 'no explicit flush: the per-step working set (X,H1,E,dE,PD activations) exceeds the 126 MB L2'}
 
 

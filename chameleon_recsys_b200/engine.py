@@ -68,6 +68,8 @@ class NarEngine:
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         self.rank = torch.distributed.get_rank(process_group) if process_group is not None else 0
+        # data parallel: contiguous session shards with equal numbers of valid positions (dp.shard_bounds); 0 = equal session counts
+        self.dp_balance = os.environ.get('NAR_DP_BALANCE', '1') == '1'
         self.C, self.H, self.Hp, self.layers = layout.C, layout.H, layout.Hp, layout.layers
         self.V = plan.num_items
         # per-unique-id CAR layer 1 (exact; csrc/car.cu).  NAR_DEDUP=0 materialises every candidate row instead.
@@ -328,7 +330,7 @@ class NarEngine:
             if buffer.size != self.buf_len:
                 raise ValueError('recent-clicks buffer has %d entries, engine was built for %d' % (buffer.size, self.buf_len))
         # this rank's sessions + compact valid positions (session-major; flat index into the GLOBAL [Bg*T] arrays)
-        sh = shard_sessions(np.asarray(features['session_size']), T, self.world, self.rank)
+        sh = shard_sessions(np.asarray(features['session_size']), T, self.world, self.rank, balance=self.dp_balance)
         s0, per, lens, L, L_global = sh['s0'], sh['per'], sh['lens'], sh['L'], sh['L_global']
         sess_off, pos_idx = sh['sess_off'], sh['pos_idx']
         all_items = np.concatenate([item_clicked, np.asarray(labels['label_last_item'], dtype=np.int64).reshape(Bg, 1)], axis=1)
@@ -353,7 +355,8 @@ class NarEngine:
             offs[name] = (off, arr.size, dt, arr.shape)
             off += arr.size * np.dtype(dt).itemsize
         total = round_up(off, 16)
-        worst = total + 4 * (per * T - pos_idx.size) + 64       # pos_idx is the only part whose size varies step to step
+        # pos_idx and (balanced shards: `per` varies) sess_off are the only parts whose size varies step to step
+        worst = total + 4 * (Bg * T - pos_idx.size) + 4 * (Bg - per) + 64
         pin = self._pin(slot, worst)
         busy = self._pin_events.get(slot)
         if busy is not None:

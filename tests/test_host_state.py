@@ -212,3 +212,38 @@ def test_native_update_from_batch_equals_hook_spec():
     before = a.pop_recent_clicks_buffer.copy()
     a.update_from_batch(z, z, np.zeros_like(l['label_last_item']))          # all padding: state untouched
     assert np.array_equal(before, a.pop_recent_clicks_buffer)
+
+
+def test_shard_bounds_balanced_and_complete():
+    """dp.shard_bounds / shard_sessions: the shards are contiguous, disjoint, cover every session, never empty, are the same
+    on every rank, and hold (nearly) equal numbers of valid positions; the union of the ranks' position lists is the
+    single-rank list (so the summed loss / gradients are those of the global batch whatever the split)."""
+    from chameleon_recsys_b200.dp import shard_bounds, shard_sessions
+    rng = np.random.default_rng(5)
+    T = 20
+    for world in (1, 2, 3, 8):
+        for Bg in (world, 17, 256, 2048):
+            if Bg < world:
+                continue
+            size = rng.geometric(0.35, Bg) + 1                         # session_size incl. the label click
+            size[rng.random(Bg) < 0.1] = 1                             # sessions without a valid position
+            lens = np.clip(size - 1, 0, T)
+            b = shard_bounds(lens, world)
+            assert b[0] == 0 and b[-1] == Bg and (np.diff(b) >= 1).all()
+            full = shard_sessions(size, T, 1, 0)
+            parts = [shard_sessions(size, T, world, r) for r in range(world)]
+            assert [p['s0'] for p in parts] == list(b[:-1]) and [p['per'] for p in parts] == list(np.diff(b))
+            assert np.array_equal(np.concatenate([p['pos_idx'] for p in parts]), full['pos_idx'])
+            assert sum(p['L'] for p in parts) == full['L'] == parts[0]['L_global']
+            for p in parts:
+                assert p['sess_off'][-1] == p['L'] and len(p['sess_off']) == p['per'] + 1
+            if Bg >= 256:
+                Ls = np.array([p['L'] for p in parts], dtype=np.float64)
+                assert Ls.max() <= Ls.mean() + T                       # within one session of the mean
+    # equal-count split on request (and its divisibility rule)
+    assert list(shard_bounds(np.ones(8, np.int64), 4, balance=False)) == [0, 2, 4, 6, 8]
+    with pytest.raises(ValueError):
+        shard_bounds(np.ones(9, np.int64), 4, balance=False)
+    with pytest.raises(ValueError):
+        shard_bounds(np.ones(3, np.int64), 4)
+    assert list(shard_bounds(np.zeros(5, np.int64), 2)) == [0, 2, 5]    # nothing to balance: near-equal counts

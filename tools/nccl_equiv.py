@@ -51,13 +51,17 @@ def main():
         for f, l, buf, pop in batches:
             out = eng.train_step(f, l, buf, pop)
             losses.append((out['xe_loss'], out['reg_loss']))
-            negs.append(out['negatives'].clone())
+            negs.append((out['negatives'].clone(), out['stage']['s0'], out['stage']['Bg']))
         torch.cuda.synchronize()
         return eng, losses, negs
 
     eng_n, loss_n, neg_n = run(dist.group.WORLD)
-    gathered = [torch.zeros_like(neg_n[-1]) for _ in range(world)]
-    dist.all_gather(gathered, neg_n[-1])
+    # the shards are balanced by valid positions, so their session counts differ: every rank drops its negatives into
+    # its rows of a zero [Bg, T, K] tensor and the sum over ranks is the global array
+    neg_r, s0_r, Bg_r = neg_n[-1]
+    neg_all = torch.zeros((Bg_r,) + tuple(neg_r.shape[1:]), dtype=neg_r.dtype, device=neg_r.device)
+    neg_all[s0_r:s0_r + neg_r.shape[0]] = neg_r
+    dist.all_reduce(neg_all)
     res = None
     if rank == 0:
         eng_1, loss_1, neg_1 = run(None)
@@ -68,7 +72,7 @@ def main():
                'loss_n': loss_n, 'loss_1': loss_1,
                'loss_rel_max': max(abs(a[0] - b[0]) / abs(b[0]) for a, b in zip(loss_n, loss_1)),
                'reg_rel_max': max(abs(a[1] - b[1]) / max(abs(b[1]), 1e-30) for a, b in zip(loss_n, loss_1)),
-               'negatives_equal': bool(torch.equal(torch.cat(gathered, 0), neg_1[-1])),
+               'negatives_equal': bool(torch.equal(neg_all, neg_1[-1][0])),
                'grad_rel_max_last_step': float((g_n - g_1).abs().max()) / scale,
                'param_diff_median': float(dp.median()), 'param_diff_max': float(dp.max()),
                'param_diff_p999': float(torch.quantile(dp[::7].float(), 0.999)), 'lr': pb.hp.learning_rate}

@@ -271,9 +271,6 @@ int run_step(nar_engine* e, const nar_step_io* io, cudaStream_t main) {
 
   // ---- session branch: RNN (nar_model.py:408, :1308-1342) + FC1 / FC2 (:410-438) on the L clicked rows
   auto session_branch = [&](cudaStream_t st) {
-    // CAR of the L clicked rows (feeds the RNN only; backward reads H1 / E of these rows much later)
-    s.fwd(sb.X, Fp, c.off_W1, C, c.off_b1, sb.H1, C, L, C, Fp, NAR_ACT_LEAKY_RELU, st);
-    s.fwd(sb.H1, C, c.off_W2, C, c.off_b2, sb.E, C, L, C, C, NAR_ACT_TANH, st);
     const float* rnn_in = sb.E; int64_t n_in = C;
     for (int i = 0; i < c.layers; ++i) {
       if (c.rnn_cell == 1) {
@@ -295,9 +292,11 @@ int run_step(nar_engine* e, const nar_step_io* io, cudaStream_t main) {
     s.fwd(sb.F1, 512, c.off_W4, C, c.off_b4, sb.PR, C, L, C, 512, NAR_ACT_TANH, st);
   };
 
-  // ---- CAR (nar_model.py:374-405): the whole session branch (CAR of the clicked rows -> RNN -> FC) runs on the auxiliary
-  // stream under the candidates' layer-1 pieces and layer-2 GEMM
+  // ---- CAR (nar_model.py:374-405): the clicked rows first, so that the session branch can run under the candidates
+  // (moving these two GEMMs into the session branch as well was measured neutral and is not used: DESIGN.md section 6)
   float* H1c = sb.H1 + L * C; float* Ec = sb.E + L * C;
+  s.fwd(sb.X, Fp, c.off_W1, C, c.off_b1, sb.H1, C, L, C, Fp, NAR_ACT_LEAKY_RELU, main);
+  s.fwd(sb.H1, C, c.off_W2, C, c.off_b2, sb.E, C, L, C, C, NAR_ACT_TANH, main);
   { cudaStream_t st = s.fork(); session_branch(st); }
   if (c.dedup) {
     s.fwd(sb.X + L * Fp, Fp, c.off_W1, C, c.off_b1, sb.PP, C, L, C, Fp, NAR_ACT_NONE, main);                       // positives: full rows

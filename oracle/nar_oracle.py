@@ -4,13 +4,22 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl refere
 may import this module; the product path never does and fails loudly without its CUDA
 library.
 
-parity unpinned: the reference arithmetic lives in TensorFlow 1.12.3 (requirements.txt:5),
-which cannot be installed here (Python 3.12, no network), and the reference has no test,
-golden vector or fixture for logits / loss / gradients / Adam.  This
-file is therefore a line-by-line restatement of the graph, pinned only by (i) hand-derived
-known answers (tests/test_oracle.py), (ii) finite-difference gradients, (iii) invariants from
-the code; its evaluation metrics (HR@n / MRR@n) ARE pinned to the reference's own numpy classes
-(tests/golden/make_metrics_golden.py).  Every function cites the lines it follows.
+Pinning.  The reference arithmetic lives in TensorFlow 1.12.3 (requirements.txt:5), which
+cannot be installed here (Python 3.12, no network), and the reference holds no test, golden vector or fixture for
+logits / loss / gradients / Adam.  What this file is checked against:
+ (a) outputs of the reference's OWN model code: nar_model.py's NARModuleModel is imported unmodified and its
+     constructor executed on an eager stand-in for the TF-1.x API (tests/golden/tf1_shim.py, generator
+     tests/golden/make_model_golden.py, fixtures tests/golden/model_golden.npz); tests/test_oracle_reference_model.py
+     compares logits, loss, the intermediates the reference exposes, every gradient, the first Adam step, and the
+     EVAL ranking / recall@n / MRR@n (train, float32, cold start, novelty regulariser, 2 RNN layers, eval): 1e-7 in
+     float64.  That pins the WIRING to the reference.  The per-op TF kernel semantics inside the stand-in (moments,
+     leaky_relu, UGRNNCell, dynamic_rnn, AdamOptimizer ...) are a restatement of the TF documentation, so "what
+     TensorFlow itself would compute" remains unpinned;
+ (b) hand-derived known answers (tests/test_oracle.py), finite-difference gradients, invariants from the code;
+ (c) the evaluation metrics (HR@n / MRR@n) against the reference's own numpy classes
+     (tests/golden/make_metrics_golden.py).
+The GRU cell, dropout masks and the cosine scorer are switches the reference does not contain as running code: (b) only.
+Every function cites the lines it follows.
 
 Restated: nar_module/nar/nar_model.py:219-245 (inputs/masks), :730-773 (get_features),
 :887-907 (scale/centre), :921-994 (item features), :996-1039 (normalisation), :1055-1089

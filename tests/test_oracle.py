@@ -1,5 +1,6 @@
 """Pins for the float oracle (oracle/nar_oracle.py).  The reference has no test or golden vector for
-logits / loss / gradients / Adam (parity unpinned), so the oracle is pinned by
+logits / loss / gradients / Adam; besides the comparison with the reference's own graph code run on a
+TF-API stand-in (tests/test_oracle_reference_model.py) the oracle is pinned here by
 (1) an independent scalar restatement of Appendix A on a hand-sized case with integer-valued weights,
 (2) closed-form known answers (UGRNN cell, TF-Adam first step, l2 regulariser),
 (3) finite-difference gradients in float64, (4) invariants of the reference code."""

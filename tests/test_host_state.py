@@ -247,3 +247,29 @@ def test_shard_bounds_balanced_and_complete():
     with pytest.raises(ValueError):
         shard_bounds(np.ones(3, np.int64), 4)
     assert list(shard_bounds(np.zeros(5, np.int64), 2)) == [0, 2, 5]    # nothing to balance: near-equal counts
+
+
+def test_hook_matches_reference_hook():
+    """ItemsStateUpdaterHook.before_run / after_run + ClickedItemsState (the product's C pass) against the REFERENCE hook
+    and state class run over the same training batches (tests/golden/make_hook_golden.py: nar_model.py:1435-1470 feed,
+    :1635-1650 flattening of [clicked | last label] with the label click borrowing the session's last timestamp)."""
+    from chameleon_recsys_b200.hparams import ModeKeys
+    from chameleon_recsys_b200.nar_model import ItemsStateUpdaterHook
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'hook_golden.npz'))
+    for ci in range(2):
+        hours, max_size, n_norm, V = d['c%d_cfg' % ci]
+        state = ClickedItemsState(float(hours), int(max_size), int(n_norm), int(V))
+        hook = ItemsStateUpdaterHook(ModeKeys.TRAIN, None, 3, state)
+        hook.begin()
+        for step in range(5):
+            feed = hook.before_run(None)
+            assert np.array_equal(feed['pop_recent_items_buffer'], d['c%d_feed_buffer_%d' % (ci, step)])
+            assert np.array_equal(np.asarray(feed['articles_recent_pop_norm']), d['c%d_feed_pop_norm_%d' % (ci, step)])
+            hook.after_run(None, {'clicked_items': d['c%d_item_clicked_%d' % (ci, step)],
+                                  'clicked_timestamps': d['c%d_event_timestamp_%d' % (ci, step)],
+                                  'last_item_label': d['c%d_label_last_item_%d' % (ci, step)]})
+            assert np.array_equal(state.pop_recent_clicks_buffer, d['c%d_buffer_%d' % (ci, step)]), (ci, step)
+            assert np.array_equal(state.get_articles_recent_pop(), d['c%d_recent_pop_%d' % (ci, step)])
+            assert np.array_equal(state.get_articles_recent_pop_norm(), d['c%d_pop_norm_%d' % (ci, step)])      # float64, bit-exact
+            assert np.array_equal(state.get_articles_pop(), d['c%d_pop_%d' % (ci, step)])
+        hook.end()

@@ -11,14 +11,15 @@ logits / loss / gradients / Adam.  What this file is checked against:
      constructor executed on an eager stand-in for the TF-1.x API (tests/golden/tf1_shim.py, generator
      tests/golden/make_model_golden.py, fixtures tests/golden/model_golden.npz); tests/test_oracle_reference_model.py
      compares logits, loss, the intermediates the reference exposes, every gradient, the first Adam step, and the
-     EVAL ranking / recall@n / MRR@n (train, float32, cold start, novelty regulariser, 2 RNN layers, eval): 1e-7 in
-     float64.  That pins the WIRING to the reference.  The per-op TF kernel semantics inside the stand-in (moments,
+     EVAL ranking / recall@n / MRR@n (train, float32, cold start, novelty regulariser, 2 RNN layers, dropout with the
+     reference run's masks handed over, eval): 1e-7 in float64.  That pins the WIRING to the reference.  The per-op TF kernel semantics inside the stand-in (moments,
      leaky_relu, UGRNNCell, dynamic_rnn, AdamOptimizer ...) are a restatement of the TF documentation, so "what
      TensorFlow itself would compute" remains unpinned;
  (b) hand-derived known answers (tests/test_oracle.py), finite-difference gradients, invariants from the code;
  (c) the evaluation metrics (HR@n / MRR@n) against the reference's own numpy classes
      (tests/golden/make_metrics_golden.py).
-The GRU cell, dropout masks and the cosine scorer are switches the reference does not contain as running code: (b) only.
+The GRU cell and the cosine scorer are switches the reference does not contain as running code: (b) only.  Dropout: the
+sites and scaling are pinned by (a); the masks themselves are this repo's counter-based spec (oracle/dropout_ref.py).
 Every function cites the lines it follows.
 
 Restated: nar_module/nar/nar_model.py:219-245 (inputs/masks), :730-773 (get_features),
@@ -81,6 +82,7 @@ class NarOracle:
         # internal (HBM) column -> logical column of the product's feature rows: the dropout spec is indexed by the former
         self.int2log = None if int2log is None else np.asarray(int2log, dtype=np.int64)
         self._drop = None          # (step,) while a training forward with dropout runs
+        self.mask_override = None
         self._kinks = None
         self.V = int(articles_features_config['article_id']['cardinality'])
         self.adam_m: Dict[str, torch.Tensor] = {}
@@ -193,10 +195,15 @@ class NarOracle:
         return torch.cat(feats, dim=-1)
 
     # ------------------------------------------------------------------ dropout (spec: oracle/dropout_ref.py)
-    def _dropout(self, x, tensor_id, row_key, feature_rows=False):
-        """tf.layers.dropout(rate = 1 - keep_prob, training=True) with the counter-based masks of dropout_ref."""
+    def _dropout(self, x, tensor_id, row_key, feature_rows=False, t=None):
+        """tf.layers.dropout(rate = 1 - keep_prob, training=True) with the counter-based masks of dropout_ref.
+        ``mask_override`` (tests/test_oracle_reference_model.py): keep-masks recorded from a run of the reference code,
+        keyed by tensor id (RNN outputs: (id, time step)), in the reference's column order."""
         if self._drop is None or self.keep_prob >= 1.0:
             return x
+        if self.mask_override is not None:
+            m = self.mask_override[tensor_id if t is None else (tensor_id, t)]
+            return x * torch.as_tensor(np.asarray(m)).to(self.dtype) / self.keep_prob
         import os
         only = os.environ.get('NAR_DEBUG_DROP_ONLY')            # diagnostics: dropout at one site only (feature rows = 0)
         if only is not None and int(only) != (0 if tensor_id in (1, 2, 3) else tensor_id):
@@ -259,7 +266,7 @@ class NarOracle:
                                    self._p(base + 'candidate/bias'))
                     h = u * states[i] + (1.0 - u) * c
                     new_states.append(h)
-                    inp = h if pos_key is None else self._dropout(h, 8 + i, pos_key[:, t])
+                    inp = h if pos_key is None else self._dropout(h, 8 + i, pos_key[:, t], t=t)
                     continue
                 base = 'main/RNN/rnn/multi_rnn_cell/cell_{}/ugrnn_cell/'.format(i)
                 m = torch.cat([inp, states[i]], dim=1) @ self._p(base + 'kernel') + self._p(base + 'bias')
@@ -268,7 +275,7 @@ class NarOracle:
                 g = torch.sigmoid(g_act + 1.0)                     # forget_bias = 1.0
                 h = g * states[i] + (1.0 - g) * c
                 new_states.append(h)
-                inp = h if pos_key is None else self._dropout(h, 8 + i, pos_key[:, t])
+                inp = h if pos_key is None else self._dropout(h, 8 + i, pos_key[:, t], t=t)
             alive = (t < lengths).to(self.dtype).unsqueeze(-1)
             outs.append(inp * alive)                                # zero output past the length
             states = [alive * ns + (1.0 - alive) * s for ns, s in zip(new_states, states)]

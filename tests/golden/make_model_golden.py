@@ -56,7 +56,7 @@ def build(pb, feats, labels, buf, pop, mode, float64, preset, seed, **over):
     labs = {k: shim._t(np.asarray(v)) for k, v in labels.items()}
     train = mode == 'train'
     kw = dict(session_features_config=pb.session_features_config, articles_features_config=pb.articles_features_config,
-              batch_size=hp.batch_size, lr=hp.learning_rate, keep_prob=1.0,
+              batch_size=hp.batch_size, lr=hp.learning_rate, keep_prob=hp.dropout_keep_prob,
               negative_samples=hp.train_total_negative_samples if train else hp.eval_total_negative_samples,
               negative_sample_from_buffer=hp.train_negative_samples_from_buffer if train else hp.eval_negative_samples_from_buffer,
               content_article_embeddings_matrix=pb.content_article_embeddings_matrix, rnn_num_layers=hp.rnn_num_layers,
@@ -143,6 +143,19 @@ def run_case(name, mode='train', float64=True, warm=5, seed=3, hp_over=None, ste
         out['predicted_item_probs'] = model.predicted_item_probs.detach().numpy()
         out['recall_at_n'] = np.asarray(model.recall_at_n.detach().numpy())
         out['mrr_at_n'] = np.asarray(model.mrr.detach().numpy())
+    if S.dropout_masks:
+        # keep-masks in the order the reference applied them: input / positive / negative feature rows (nar_model.py:338,
+        # :351, :367), DropoutWrapper outputs per (time step, layer) (:1330-1333), FC1 (:417)
+        T, nl = feats['item_clicked'].shape[1], pb.hp.rnn_num_layers
+        assert len(S.dropout_masks) == 3 + T * nl + 1
+        for j, nm in enumerate(('in', 'pos', 'neg')):
+            out['mask/' + nm] = np.packbits(S.dropout_masks[j].numpy())
+            out['mask_shape/' + nm] = np.array(S.dropout_masks[j].shape)
+        rn = torch.stack(S.dropout_masks[3:3 + T * nl]).reshape(T, nl, *S.dropout_masks[3].shape)
+        out['mask/rnn'] = np.packbits(rn.numpy())
+        out['mask_shape/rnn'] = np.array(rn.shape)
+        out['mask/fc1'] = np.packbits(S.dropout_masks[-1].numpy())
+        out['mask_shape/fc1'] = np.array(S.dropout_masks[-1].shape)
     out['meta'] = np.array([mode, 'float64' if float64 else 'float32', str(warm), repr(hp_over or {})])
     return {name + '/' + k: v for k, v in out.items()}
 
@@ -162,6 +175,7 @@ def main():
     cases.update(run_case('cold64', warm=0, keep_hist=True))                                   # empty buffer: tf.cond takes the batch statistics
     cases.update(run_case('nov64', hp_over=dict(novelty_reg_factor=0.3)))
     cases.update(run_case('layers2_64', hp_over=dict(rnn_num_layers=2)))
+    cases.update(run_case('drop64', hp_over=dict(dropout_keep_prob=0.8, rnn_num_layers=2)))
     cases.update(run_case('eval64', mode='eval', steps_skip=1, keep_hist=True))
     # the variables are the same in every single-layer case (same initializer seed): stored once
     base = {k[len('train64/'):]: v for k, v in cases.items() if k.startswith('train64/var/')}

@@ -46,6 +46,7 @@ class _State:
         self.hist = []                       # (name, tensor) from tf.summary.histogram
         self.scalars = []                    # (name, tensor) from tf.summary.scalar
         self.softmax_inputs = []             # inputs of tf.nn.softmax in call order
+        self.dropout_masks = []              # keep-masks of tf.layers.dropout / DropoutWrapper in call order
         self.grads = None                    # name -> gradient (AdamOptimizer.compute_gradients)
         self.vars_after = None               # name -> value after apply_gradients
         self.adam = None
@@ -609,8 +610,9 @@ def dropout(inputs, rate=0.5, noise_shape=None, seed=None, training=False, name=
     if not training or float(rate) == 0.0:
         return x
     keep = 1.0 - float(rate)
-    mask = (torch.rand(x.shape, generator=S.rng, dtype=torch.float64) < keep).to(x.dtype)
-    return x * mask / keep
+    mask = (torch.rand(x.shape, generator=S.rng, dtype=torch.float64) < keep)
+    S.dropout_masks.append(mask.clone())
+    return x * mask.to(x.dtype) / keep
 
 
 tf.layers.dropout = dropout

@@ -175,3 +175,42 @@ def test_reference_sampler_output_has_the_properties_the_oracle_sampler_guarante
                     assert not (set(nz.tolist()) & sess)
                     assert set(nz.tolist()) <= pool
                     assert not row[len(nz):].any()            # padding (pool exhausted) only at the end
+
+
+def test_dropout_sites_match_reference_code(golden):
+    """keep_prob 0.8, two RNN layers: the reference code ran with the stand-in's random masks; the SAME masks are handed to
+    the oracle (mask_override), which must then reproduce loss, logits and gradients - i.e. dropout sits at the same five
+    sites (input / positive / negative feature rows after gamma-beta, every cell's OUTPUT but not its state, FC1) with the
+    same 1 / keep_prob scaling.  (The product's own masks are defined by oracle/dropout_ref.py's counter-based RNG.)"""
+    d = golden
+    P = 'drop64/'
+    hp_over = {'dropout_keep_prob': 0.8, 'rnn_num_layers': 2}
+    pb, orc, f, lab, neg, buf, pop, tf_vars = _load(d, 'drop64', hp_over, torch.float64)
+
+    def unpack(n):
+        shp = tuple(int(v) for v in d[P + 'mask_shape/' + n])
+        return np.unpackbits(d[P + 'mask/' + n])[:int(np.prod(shp))].reshape(shp).astype(bool)
+
+    rnn = unpack('rnn')                                      # [T, layers, B, H]
+    over = {1: unpack('in'), 2: unpack('pos'), 3: unpack('neg'), 4: unpack('fc1')}
+    for t in range(rnn.shape[0]):
+        for i in range(rnn.shape[1]):
+            over[(8 + i, t)] = rnn[t, i]
+    assert 0.75 < over[3].mean() < 0.85
+    orc.mask_override = over
+    o = orc.forward(f, lab, neg, buf, pop, train_step=1)
+    mask = o['mask'].numpy().astype(bool)
+    assert abs(float(o['total_loss'].detach()) - float(d[P + 'total_loss'])) / abs(float(d[P + 'total_loss'])) < 1e-7
+    assert _rel(o['logits'].detach().numpy()[mask], d[P + 'logits_scaled'][mask]) < 1e-7
+    grads = orc.compute_gradients(o)
+    gmax = max(float(np.abs(d[k]).max()) for k in d.files if k.startswith(P + 'grad/'))
+    for n_tf in tf_vars:
+        g_ref = d[P + 'grad/' + n_tf]
+        g_orc = grads[_tf_name_to_layout(n_tf)].detach().numpy()
+        if g_ref.shape != g_orc.shape:
+            g_orc = g_orc.reshape(-1)[::THIN]
+        assert float(np.abs(g_orc - g_ref).max()) < 2e-6 * gmax, n_tf
+    # and without the masks the result differs (the check above is not vacuous)
+    orc.mask_override = None
+    o2 = orc.forward(f, lab, neg, buf, pop, train_step=1)
+    assert abs(float(o2['total_loss'].detach()) - float(d[P + 'total_loss'])) / abs(float(d[P + 'total_loss'])) > 1e-4

@@ -22,6 +22,24 @@ import numpy as np
 STATE_FIELDS = ('articles_pop', 'articles_recent_pop', 'articles_recent_pop_norm', 'pop_recent_clicks_buffer')
 
 
+# TensorFlow names the variables of a tf.layers.Dense object after the variable scope of its FIRST call, not the scope it
+# is constructed in (found by running the reference's nar_model.py: tests/golden/make_model_golden.py).  plan.ParamLayout
+# uses the constructing scope; tensors exported from a real TF checkpoint under their TF names load through this table.
+TF_SCOPE_ALIASES = (
+    ('main/user_personalized_contextual_article_embedding/input/CAR_representation/', 'main/CAR/CAR_representation/'),
+    ('main/recommendations_ranking/cos_sim_positive/matching_dense_layer_', 'main/recommendations_ranking/matching_dense_layer_'),
+)
+
+
+def layout_name(tf_name: str) -> str:
+    """TF variable name (optionally with the ':0' tensor suffix) -> the name plan.ParamLayout uses."""
+    name = tf_name[:-2] if tf_name.endswith(':0') else tf_name
+    for tf_prefix, ours in TF_SCOPE_ALIASES:
+        if name.startswith(tf_prefix):
+            return ours + name[len(tf_prefix):]
+    return name
+
+
 def checkpoint_path(model_dir: str, global_step: int) -> str:
     return os.path.join(model_dir, 'model.ckpt-%d.npz' % int(global_step))
 
@@ -61,7 +79,7 @@ def load(path: str) -> dict:
         for k in z.files:
             if '/' in k:
                 group, name = k.split('/', 1)
-                out[group][name] = z[k]
+                out[group][layout_name(name) if group in ('params', 'adam_m', 'adam_v') else name] = z[k]
     return out
 
 

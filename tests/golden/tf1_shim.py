@@ -796,3 +796,96 @@ tf.contrib.metrics.sparse_recall_at_top_k = sparse_recall_at_top_k
 tf.metrics.mean = metrics_mean
 tf.contrib.lookup.HashTable = lambda *a, **k: None
 tf.contrib.lookup.KeyValueTensorInitializer = lambda *a, **k: None
+
+# ---------------------------------------------------------------------------------------------- tf.data / example parsing
+# (for /root/reference/nar_module/nar/datasets.py: TFRecordDataset -> map(parse_sequence_example) -> padded_batch -> map)
+tf.data = _mod('tensorflow.data')
+tf.FixedLenFeature = collections.namedtuple('FixedLenFeature', ['shape', 'dtype'])
+tf.FixedLenSequenceFeature = lambda shape, dtype, **k: types.SimpleNamespace(shape=shape, dtype=dtype)
+tf.convert_to_tensor = lambda x, **k: _t(x)
+
+
+def _np_dtype(dtype):
+    return {torch.int64: np.int64, torch.int32: np.int32, torch.float32: np.float32, torch.float64: np.float64}[dtype]
+
+
+def parse_single_sequence_example(serialized, context_features=None, sequence_features=None, example_name=None, name=None):
+    """S.example_decoder(bytes) -> (context {name: values}, feature_lists {name: values per step}) does the protobuf part
+    (the generator plugs in Google's protobuf runtime); FixedLenFeature([]) is a scalar, FixedLenSequenceFeature([]) a vector"""
+    ctx, seqs = S.example_decoder(serialized)
+    context_parsed = {k: torch.as_tensor(np.asarray(ctx[k], dtype=_np_dtype(spec.dtype)).reshape(()))
+                      for k, spec in (context_features or {}).items()}
+    sequence_parsed = {k: torch.as_tensor(np.asarray(seqs[k], dtype=_np_dtype(spec.dtype)).reshape(-1))
+                       for k, spec in (sequence_features or {}).items()}
+    return context_parsed, sequence_parsed
+
+
+tf.parse_single_sequence_example = parse_single_sequence_example
+
+
+class Dataset:
+    def __init__(self, gen_fn):
+        self._gen = gen_fn
+
+    def __iter__(self):
+        return iter(self._gen())
+
+    def map(self, fn, num_parallel_calls=None):
+        src = self._gen
+        return Dataset(lambda: (fn(x) for x in src()))
+
+    def prefetch(self, n):
+        return self
+
+    def padded_batch(self, batch_size, padded_shapes, padding_values=None, drop_remainder=False):
+        """tf.data padded_batch: a [None] component is zero-padded to the longest of the batch, then everything is stacked"""
+        src = self._gen
+
+        def gen():
+            it = iter(src())
+            while True:
+                chunk = []
+                for x in it:
+                    chunk.append(x)
+                    if len(chunk) == batch_size:
+                        break
+                if not chunk or (drop_remainder and len(chunk) < batch_size):
+                    return
+                out = {}
+                for k in chunk[0]:
+                    vals = [_t(c[k]) for c in chunk]
+                    n = max(v.shape[0] for v in vals)
+                    out[k] = torch.stack([torch.cat([v, torch.zeros(n - v.shape[0], dtype=v.dtype)]) for v in vals])
+                yield out
+        return Dataset(gen)
+
+    def make_one_shot_iterator(self):
+        it = iter(self._gen())
+        return types.SimpleNamespace(get_next=lambda: next(it))
+
+
+def _read_tfrecords(path, gzip_compressed):
+    import gzip
+    import struct
+    with (gzip.open(path, 'rb') if gzip_compressed else open(path, 'rb')) as f:
+        while True:
+            head = f.read(12)                         # uint64 length + masked crc32c of the length (not verified here)
+            if len(head) < 12:
+                return
+            n = struct.unpack('<Q', head[:8])[0]
+            data = f.read(n)
+            f.read(4)                                 # masked crc32c of the data
+            yield data
+
+
+def TFRecordDataset(filenames, compression_type=None, **k):
+    import glob as _glob
+    names = [filenames] if isinstance(filenames, str) else list(filenames)
+    files = []
+    for n in names:
+        files.extend(sorted(_glob.glob(n)) or [n])
+    return Dataset(lambda: (r for p in files for r in _read_tfrecords(p, compression_type == 'GZIP')))
+
+
+tf.data.TFRecordDataset = TFRecordDataset
+tf.data.Dataset = Dataset

@@ -156,3 +156,31 @@ def test_input_fn_from_tfrecord_files_equals_in_memory(tmp_path):
             assert np.array_equal(la[k], lb[k]), k
         n += 1
     assert n == 3
+
+
+def test_input_pipeline_matches_reference_pipeline():
+    """prepare_dataset_iterator on a TFRecord file against the batches the REFERENCE pipeline produced from the same file
+    (datasets.py make_dataset imported unmodified, run on the tf.data subset of tests/golden/tf1_shim.py with Google's
+    protobuf runtime as the example decoder; tests/golden/make_dataset_golden.py): keys, dtypes, shapes, padding, the
+    label shift, truncation and the last partial batch."""
+    from chameleon_recsys_b200.datasets import prepare_dataset_iterator
+    from chameleon_recsys_b200.harness import make_problem
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    d = np.load(os.path.join(here, 'dataset_golden.npz'))
+    cfg = make_problem('tiny', profile='B').session_features_config
+    for ci in range(3):
+        batch_size, trunc, nb = (int(v) for v in d['c%d_cfg' % ci])
+        it = prepare_dataset_iterator(os.path.join(here, 'sessions_golden.tfrecord.gz'), cfg, batch_size=batch_size,
+                                      truncate_session_length=trunc)
+        n = 0
+        for feats, labels in it:
+            ref_f = {k.split('/', 1)[1]: d[k] for k in d.files if k.startswith('c%d_b%d_feat/' % (ci, n))}
+            ref_l = {k.split('/', 1)[1]: d[k] for k in d.files if k.startswith('c%d_b%d_label/' % (ci, n))}
+            assert set(feats) == set(ref_f) and set(labels) == set(ref_l)
+            for k in ref_f:
+                assert feats[k].dtype == ref_f[k].dtype and feats[k].shape == ref_f[k].shape, (k, feats[k].shape, ref_f[k].shape)
+                assert np.array_equal(feats[k], ref_f[k]), k
+            for k in ref_l:
+                assert labels[k].dtype == ref_l[k].dtype and np.array_equal(labels[k], ref_l[k]), k
+            n += 1
+        assert n == nb

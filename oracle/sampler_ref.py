@@ -33,7 +33,9 @@ specification (identical code runs in the CUDA kernel):
 parity: the reference holds no golden vectors for sampled indices; the
 pin is (i) the reference's 8 property tests (ported in tests/test_sampler_oracle.py),
 (ii) inclusion-frequency fixtures generated from the reference's own numpy sampler
-(tests/golden/make_sampler_golden.py).
+(tests/golden/make_sampler_golden.py), (iii) inclusion frequencies of the reference's TF sampler
+code itself (nar_model.py:1220-1304 imported unmodified, run on the TF-API stand-in
+tests/golden/tf1_shim.py: tests/golden/make_sampler_tf_golden.py).
 """
 from __future__ import annotations
 

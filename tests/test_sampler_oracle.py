@@ -151,3 +151,29 @@ def test_inclusion_frequencies_match_reference_sampler():
     se = np.sqrt(ref * (1 - ref) / trials + ref * (1 - ref) / g['trials']) + 1e-9
     z = np.abs(freq - ref) / se
     assert z.max() < 4.5, (z.max(), freq, ref)
+
+
+def test_inclusion_frequencies_match_reference_tf_sampler():
+    """Distribution of the whole training-graph sampler (buffer sample -> candidate pool with repetitions, truncated to
+    K*20 -> per-session exclusion -> per-click shuffle / unique / first K) against the REFERENCE's TF sampler code run
+    3000 times on the TF-API stand-in (tests/golden/make_sampler_tf_golden.py): same support, and per (click, item)
+    inclusion frequencies within sampling noise (two independent 3000-trial estimates: z = diff / sqrt(2 p (1-p) / N))."""
+    d = np.load(os.path.join(HERE, 'golden', 'sampler_tf_freq.npz'))
+    allc, buf, V = d['all_clicked'], d['buffer'], int(d['V'])
+    B, T1 = allc.shape
+    for ci in range(2):
+        K, nfb, n_ref = (int(v) for v in d['c%d_cfg' % ci])
+        N = 3000
+        counts = np.zeros((B, T1 - 1, V))
+        for step in range(1, N + 1):
+            neg = sampler_ref.sample_negatives(allc, buf, K, nfb, 1234, step)
+            for b in range(B):
+                for t in range(T1 - 1):
+                    row = neg[b, t]
+                    counts[b, t, row[row != 0]] += 1
+        f, g = counts / N, d['c%d_freq' % ci]
+        assert np.array_equal(f > 0, g > 0)                      # same candidates are reachable for every click
+        p = (f + g) / 2
+        z = np.abs(f - g)[p > 0] / np.sqrt(p * (1 - p) * (1.0 / N + 1.0 / n_ref))[p > 0]
+        assert z.max() < 4.5 and (z ** 2).mean() < 1.6, (ci, z.max(), (z ** 2).mean())
+        assert float(d['c%d_pad_per_trial' % ci]) == 0.0          # (the scenario never runs out of candidates)

@@ -42,6 +42,8 @@ sys.modules['refnar'] = pkg
 ref = importlib.import_module('refnar.nar_model')
 
 import torch  # noqa: E402
+
+torch.set_num_threads(1)      # float32 scatter-add order (embedding gradients) would otherwise vary run to run at 1e-7
 from chameleon_recsys_b200.harness import make_problem, warm_state  # noqa: E402
 
 

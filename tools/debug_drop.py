@@ -1,5 +1,6 @@
-"""Open issue: gradients of isolated steps with >= 2 RNN layers AND dropout.  Prints, per case and
-step, the forward errors and the worst gradient tensors (relative, absolute error of absolute max)."""
+"""Diagnostic used while chasing the sporadic gradient discrepancies of steps with dropout (resolved: leaky_relu kink flips,
+DESIGN.md section 3 - gradients are now compared at identical slope choices).  Prints, per case and step, the forward
+errors and the worst gradient tensors (relative, absolute error of absolute max); NAR_DEBUG_DROP_ONLY isolates one site."""
 import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -11,7 +11,7 @@ logits / loss / gradients / Adam.  What this file is checked against:
      constructor executed on an eager stand-in for the TF-1.x API (tests/golden/tf1_shim.py, generator
      tests/golden/make_model_golden.py, fixtures tests/golden/model_golden.npz); tests/test_oracle_reference_model.py
      compares logits, loss, the intermediates the reference exposes, every gradient, the first Adam step, and the
-     EVAL ranking / recall@n / MRR@n (train, float32, cold start, novelty regulariser, 2 RNN layers, dropout with the
+     EVAL ranking / recall@n / MRR@n (train, float32, cold start, novelty regulariser, 2 RNN layers, internal-feature switches, dropout with the
      reference run's masks handed over, eval): 1e-7 in float64.  That pins the WIRING to the reference.  The per-op TF kernel semantics inside the stand-in (moments,
      leaky_relu, UGRNNCell, dynamic_rnn, AdamOptimizer ...) are a restatement of the TF documentation, so "what
      TensorFlow itself would compute" remains unpinned;

@@ -119,6 +119,7 @@ def run_case(name, mode='train', float64=True, warm=5, seed=3, hp_over=None, ste
         out['var/' + n] = v.detach().numpy().astype(np.float32)          # (float32-valued by construction)
         assert np.array_equal(out['var/' + n].astype(np.float64), v.detach().numpy().astype(np.float64))
     out['reg_names'] = np.array(sorted(S.regs.keys()))
+    out['var_names'] = np.array(list(S.vars.keys()))
     out['negatives'] = model.batch_negative_items.numpy()
     out['total_loss'] = np.asarray(model.total_loss.detach().numpy())
     out['logits_scaled'] = S.softmax_inputs[0].numpy()
@@ -177,6 +178,8 @@ def main():
     cases.update(run_case('cold64', warm=0, keep_hist=True))                                   # empty buffer: tf.cond takes the batch statistics
     cases.update(run_case('nov64', hp_over=dict(novelty_reg_factor=0.3)))
     cases.update(run_case('layers2_64', hp_over=dict(rnn_num_layers=2)))
+    # internal feature switches (nar_trainer_gcom.py:218-230): recency + ACR embeddings only
+    cases.update(run_case('featoff64', hp_over=dict(enabled_internal_features=['recency', 'article_content_embeddings'])))
     cases.update(run_case('drop64', hp_over=dict(dropout_keep_prob=0.8, rnn_num_layers=2)))
     cases.update(run_case('eval64', mode='eval', steps_skip=1, keep_hist=True))
     # the variables are the same in every single-layer case (same initializer seed): stored once

@@ -52,6 +52,7 @@ def _load(d, case, hp_over, dtype):
         base = str(d[P + 'same_vars_as']) + '/'
         tf_vars.update({k[len(base) + 4:]: d[k] for k in d.files if k.startswith(base + 'var/')})
     tf_vars.update({k[len(P) + 4:]: d[k] for k in d.files if k.startswith(P + 'var/')})
+    tf_vars = {str(n): tf_vars[str(n)] for n in d[P + 'var_names']}      # the variables THIS case's graph created
     orc.set_params({_tf_name_to_layout(n): v for n, v in tf_vars.items()})
     assert set(_tf_name_to_layout(n) for n in tf_vars) == set(pb.layout.init_logical(1).keys())      # same variable set, same shapes
     for n, v in tf_vars.items():
@@ -62,7 +63,8 @@ def _load(d, case, hp_over, dtype):
 
 
 CASES = [('train64', {}, torch.float64, 1e-7), ('train32', {}, torch.float32, 2e-5), ('cold64', {}, torch.float64, 1e-7),
-         ('nov64', {'novelty_reg_factor': 0.3}, torch.float64, 1e-7), ('layers2_64', {'rnn_num_layers': 2}, torch.float64, 1e-7)]
+         ('nov64', {'novelty_reg_factor': 0.3}, torch.float64, 1e-7), ('layers2_64', {'rnn_num_layers': 2}, torch.float64, 1e-7),
+         ('featoff64', {'enabled_internal_features': ['recency', 'article_content_embeddings']}, torch.float64, 1e-7)]
 
 
 @pytest.mark.parametrize('case,hp_over,dtype,tol', CASES, ids=[c[0] for c in CASES])

@@ -889,3 +889,32 @@ def TFRecordDataset(filenames, compression_type=None, **k):
 
 tf.data.TFRecordDataset = TFRecordDataset
 tf.data.Dataset = Dataset
+
+# ---------------------------------------------------------------------------------------------- tf.flags / EstimatorSpec
+# (for /root/reference/nar_module/nar/nar_trainer_gcom.py: flag definitions at import time, nar_module_model_fn)
+tf.flags = _mod('tensorflow.flags')
+tf.flags.FLAGS = types.SimpleNamespace()
+tf.app = _mod('tensorflow.app')
+tf.app.flags = tf.flags
+tf.app.run = lambda *a, **k: None
+
+
+def _define(name, default=None, help=None, **k):
+    setattr(tf.flags.FLAGS, name, default)
+
+
+for _n in ('DEFINE_integer', 'DEFINE_float', 'DEFINE_string', 'DEFINE_boolean', 'DEFINE_bool', 'DEFINE_list'):
+    setattr(tf.flags, _n, _define)
+
+
+class EstimatorSpec:
+    def __init__(self, mode, predictions=None, loss=None, train_op=None, eval_metric_ops=None, training_chief_hooks=None,
+                 training_hooks=None, evaluation_hooks=None, **k):
+        self.mode, self.loss, self.train_op, self.eval_metric_ops = mode, loss, train_op, eval_metric_ops
+        self.training_chief_hooks, self.evaluation_hooks = training_chief_hooks, evaluation_hooks
+
+
+tf.estimator.EstimatorSpec = EstimatorSpec
+tf.estimator.Estimator = lambda *a, **k: types.SimpleNamespace(args=a, kwargs=k)
+tf.estimator.RunConfig = lambda *a, **k: types.SimpleNamespace(kwargs=k)
+tf.set_random_seed = lambda *a, **k: None

@@ -216,3 +216,20 @@ def test_dropout_sites_match_reference_code(golden):
     orc.mask_override = None
     o2 = orc.forward(f, lab, neg, buf, pop, train_step=1)
     assert abs(float(o2['total_loss'].detach()) - float(d[P + 'total_loss'])) / abs(float(d[P + 'total_loss'])) > 1e-4
+
+
+def test_reference_model_fn_accepts_this_repos_params(golden):
+    """tests/golden/make_model_fn_golden.py called the REFERENCE's nar_module_model_fn (nar_trainer_gcom.py:234-332) with the
+    params dict NARHParams.to_params builds (what this repo's build_estimator passes to its own model_fn): it accepted the
+    dict in TRAIN and EVAL and produced exactly the losses of the direct-constructor golden cases, i.e. key names, the
+    train / eval choice of sampling sizes and keep_prob = 1 in EVAL line up with the reference's trainer."""
+    import json
+    with open(os.path.join(os.path.dirname(GOLDEN), 'model_fn_golden.json')) as f:
+        g = json.load(f)
+    for mode in ('train', 'eval'):
+        assert abs(g[mode]['loss'] - float(golden[g[mode]['golden_case'] + '/total_loss'])) < 1e-12
+    assert g['eval']['eval_metric_ops'] == ['hitrate_at_n', 'mrr_at_n']
+    pb = make_problem('tiny', profile='B')
+    params = pb.hp.to_params(pb.session_features_config, pb.articles_features_config, pb.articles_metadata,
+                             pb.content_article_embeddings_matrix)
+    assert sorted(params) == g['train']['params_keys_passed']                 # the dict has not drifted since

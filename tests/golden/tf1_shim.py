@@ -1,6 +1,8 @@
-"""A small EAGER stand-in for the TensorFlow 1.x API surface that the reference NAR model uses
-(/root/reference/nar_module/nar/nar_model.py), so that the reference's OWN graph-building code can be imported and
-executed in this container (TensorFlow 1.12 cannot be installed: python 3.12, no network).
+"""A small EAGER stand-in for the TensorFlow 1.x API surface that the reference NAR module uses
+(/root/reference/nar_module/nar: nar_model.py, datasets.py, nar_trainer_gcom.py's model_fn), so that the reference's OWN
+code can be imported and executed in this container (TensorFlow 1.12 cannot be installed: python 3.12, no network).
+Users: tests/golden/make_model_golden.py (whole model graph), make_sampler_tf_golden.py (sampler distribution),
+make_hook_golden.py (SessionRunHook), make_dataset_golden.py (tf.data input pipeline), make_model_fn_golden.py (model_fn).
 
 What this is for: tests/golden/make_model_golden.py installs this module as ``tensorflow``, imports the reference's
 ``NARModuleModel`` unmodified and runs its constructor; every ``tf.*`` call computes immediately on torch-CPU tensors

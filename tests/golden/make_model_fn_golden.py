@@ -78,6 +78,17 @@ for mode, case, skip in (('train', 'train64', 0), ('eval', 'eval64', 1)):
     out[mode] = {'loss': loss, 'golden_case': case, 'params_keys_passed': sorted(k for k in params if k != 'clicked_items_state'),
                  'eval_metric_ops': sorted(spec.eval_metric_ops) if spec.eval_metric_ops else None,
                  'negatives_shape': list(hooks[0].model.batch_negative_items.shape)}
+# the trainer's feature / internal-feature configuration builders (nar_trainer_gcom.py:99-231) under a few flag settings
+cfgs = []
+for clicks, arts, internal in (([trainer.ALL_FEATURES], [trainer.ALL_FEATURES], [trainer.ALL_FEATURES]),
+                               (['time', 'location'], ['category'], ['recency', 'article_content_embeddings']),
+                               (['device'], [], ['novelty', 'item_clicked_embeddings', 'bogus'])):
+    trainer.FLAGS.enabled_clicks_input_features_groups = clicks
+    trainer.FLAGS.enabled_articles_input_features_groups = arts
+    trainer.FLAGS.enabled_internal_features = internal
+    cfgs.append({'flags': [clicks, arts, internal], 'session': trainer.get_session_features_config(),
+                 'articles': trainer.get_articles_features_config(), 'internal': trainer.get_internal_enabled_features_config()})
+out['feature_configs'] = cfgs
 with open(os.path.join(HERE, 'model_fn_golden.json'), 'w') as f:
     json.dump(out, f, indent=1)
-print(json.dumps({m: {k: v for k, v in o.items() if k != 'params_keys_passed'} for m, o in out.items()}))
+print(json.dumps({m: {k: v for k, v in o.items() if k != 'params_keys_passed'} for m, o in out.items() if m != 'feature_configs'}))

@@ -289,3 +289,26 @@ def test_checkpoint_accepts_tf_variable_names(tmp_path):
     np.savez(path, global_step=np.int64(7), **{'params/' + n: d['train64/var/' + n] for n in tf_names})
     ck = ckpt.load(path)
     assert set(ck['params'].keys()) == ours and ck['global_step'] == 7
+
+
+def test_feature_config_builders_match_reference_trainer():
+    """hparams.get_*_features_config against the reference trainer's builders (nar_trainer_gcom.py:99-231, run by
+    tests/golden/make_model_fn_golden.py) under three flag settings.  The one documented difference: this repo always sets
+    the article_id / item_clicked cardinality to the catalogue size (the gcom trainer hard-codes 364047 for item_clicked and
+    forgets article_id, which nar_model.py:183 reads)."""
+    import json
+    from chameleon_recsys_b200.hparams import (get_articles_features_config, get_internal_enabled_features_config,
+                                               get_session_features_config)
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'model_fn_golden.json')) as f:
+        g = json.load(f)['feature_configs']
+    assert len(g) == 3
+    for c in g:
+        clicks, arts, internal = c['flags']
+        ours_s = get_session_features_config(364047, clicks)
+        assert ours_s == c['session']
+        assert list(ours_s['sequence_features']) == list(c['session']['sequence_features'])      # order = feature column order
+        ours_a = get_articles_features_config(1000, arts)
+        ref_a = dict(c['articles'])
+        ref_a['article_id'] = dict(ref_a['article_id'], cardinality=1000)
+        assert ours_a == ref_a and list(ours_a) == list(ref_a)
+        assert get_internal_enabled_features_config(internal) == c['internal']

@@ -11,14 +11,15 @@ logits / loss / gradients / Adam.  What this file is checked against:
      constructor executed on an eager stand-in for the TF-1.x API (tests/golden/tf1_shim.py, generator
      tests/golden/make_model_golden.py, fixtures tests/golden/model_golden.npz); tests/test_oracle_reference_model.py
      compares logits, loss, the intermediates the reference exposes, every gradient, the first Adam step, and the
-     EVAL ranking / recall@n / MRR@n (train, float32, cold start, novelty regulariser, 2 RNN layers, internal-feature switches, dropout with the
+     EVAL ranking / recall@n / MRR@n (train, float32, cold start, novelty regulariser, 2 RNN layers, internal-feature switches, GRU cell substituted, dropout with the
      reference run's masks handed over, eval): 1e-7 in float64.  That pins the WIRING to the reference.  The per-op TF kernel semantics inside the stand-in (moments,
      leaky_relu, UGRNNCell, dynamic_rnn, AdamOptimizer ...) are a restatement of the TF documentation, so "what
      TensorFlow itself would compute" remains unpinned;
  (b) hand-derived known answers (tests/test_oracle.py), finite-difference gradients, invariants from the code;
  (c) the evaluation metrics (HR@n / MRR@n) against the reference's own numpy classes
      (tests/golden/make_metrics_golden.py).
-The GRU cell and the cosine scorer are switches the reference does not contain as running code: (b) only.  Dropout: the
+The cosine scorer is a switch the reference does not contain as running code: (b) only.  The GRU branch is placed in the
+graph by the reference code (the stand-in substitutes its GRUCell for UGRNNCell); the cell formula is the TF docs', restated.  Dropout: the
 sites and scaling are pinned by (a); the masks themselves are this repo's counter-based spec (oracle/dropout_ref.py).
 Every function cites the lines it follows.
 

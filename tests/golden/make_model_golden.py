@@ -84,7 +84,11 @@ def _thin(a, full):
     return a if (full or a.size <= 20000) else np.ascontiguousarray(a.reshape(-1)[::THIN])
 
 
-def run_case(name, mode='train', float64=True, warm=5, seed=3, hp_over=None, steps_skip=0, keep_adam=False, full_grads=False, keep_hist=False):
+def run_case(name, mode='train', float64=True, warm=5, seed=3, hp_over=None, steps_skip=0, keep_adam=False, full_grads=False, keep_hist=False,
+             gru=False):
+    # gru: the cell nar_model.py:1315 keeps commented out (north_star's "session GRU").  The reference file is not edited:
+    # the stand-in hands out its GRUCell when the code asks for tf.contrib.rnn.UGRNNCell - the effect of un-commenting :1315
+    shim.tf.contrib.rnn.UGRNNCell = shim.GRUCell if gru else shim.UGRNNCell
     pb = make_problem('tiny', profile='B', **(hp_over or {}))
     if warm:
         warm_state(pb, warm)
@@ -180,6 +184,7 @@ def main():
     cases.update(run_case('layers2_64', hp_over=dict(rnn_num_layers=2)))
     # internal feature switches (nar_trainer_gcom.py:218-230): recency + ACR embeddings only
     cases.update(run_case('featoff64', hp_over=dict(enabled_internal_features=['recency', 'article_content_embeddings'])))
+    cases.update(run_case('gru64', hp_over=dict(rnn_num_layers=2), gru=True))
     cases.update(run_case('drop64', hp_over=dict(dropout_keep_prob=0.8, rnn_num_layers=2)))
     cases.update(run_case('eval64', mode='eval', steps_skip=1, keep_hist=True))
     # the variables are the same in every single-layer case (same initializer seed): stored once

@@ -64,7 +64,10 @@ def _load(d, case, hp_over, dtype):
 
 CASES = [('train64', {}, torch.float64, 1e-7), ('train32', {}, torch.float32, 2e-5), ('cold64', {}, torch.float64, 1e-7),
          ('nov64', {'novelty_reg_factor': 0.3}, torch.float64, 1e-7), ('layers2_64', {'rnn_num_layers': 2}, torch.float64, 1e-7),
-         ('featoff64', {'enabled_internal_features': ['recency', 'article_content_embeddings']}, torch.float64, 1e-7)]
+         ('featoff64', {'enabled_internal_features': ['recency', 'article_content_embeddings']}, torch.float64, 1e-7),
+         # the reference code with the stand-in's GRUCell in place of UGRNNCell (= un-commenting nar_model.py:1315): pins where
+         # the oracle's GRU branch sits in the graph; the cell formula itself is the TF documentation's, restated twice
+         ('gru64', {'rnn_num_layers': 2, 'rnn_cell': 'gru'}, torch.float64, 1e-7)]
 
 
 @pytest.mark.parametrize('case,hp_over,dtype,tol', CASES, ids=[c[0] for c in CASES])
